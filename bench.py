@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- IDW gridding throughput on B200 (BASELINE.json metric: G cell*point evals/s, FP64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--precision fp64|fp32]
+    python bench.py --impl reference ...        # the reference's CPU algorithm (oracle port) on the host cores
+    torchrun ... bench.py --gpus N ...          # one rank per GPU (the driver's launch for N > 1)
+
+A step = one pass of the hot path (every cell of this rank's row band x every point x all exponents of
+the workload) on synthetic data of the named shape.  `value` is the whole-job throughput with inputs
+resident in HBM (CUDA events on the launching stream, max over ranks); `e2e` is the same metric
+through the C ABI with HOST buffers (v2r_idw_solve: H2D of the points, kernels, gather, D2H of the
+rasters all inside the timed region).  Weak scaling: every rank keeps one workload-sized row band
+(the grid grows by N in y), no data-path collective in the timed region -- the point broadcast and
+band gather belong to e2e.  See DESIGN.md section 6 for the roofline arithmetic.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "IDW cell-point evals/s (FP64)"
+UNIT = "G evals/s"
+NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 FP64 lanes x 2 x 1.965 GHz
+# algorithmic FP64-pipe instruction slots per cell-point pair
+ALGO_SLOTS = {"c2": 8.0, "c3": 38.0, "c4": 8.0, "c5": 24.0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--band-rows", type=int, default=0, help="rows of the rank's band per step (0 = the whole workload grid)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_sample(name, seconds, scale_rows=1):
+    """Times the oracle (CPU restatement of the reference, `-c` concurrent mode) on a bounded sample of
+    the workload: rows [0, R) of the same grid against the full point set, all host threads."""
+    from oracle import oracle as O
+    from v2r_b200 import workloads
+    x, y, w, xi, yi, exps = workloads.make(name, scale_rows=scale_rows)
+    oi = lambda i: O.Info(i.min, i.max, i.step)  # noqa: E731
+    ps = O.make_coord_space(x, y, w, oi(xi), oi(yi))
+    rows, cols = O.get_dimensions(oi(xi), oi(yi))
+    threads = O.num_threads()
+    n = len(ps)
+    E = len(exps)
+
+    def run(nrows):
+        # chunk width: the CLI default 200 (cmd/idw.go:53) unless that leaves cores without a job
+        chunk_c = 200
+        while chunk_c > 8 and nrows * ((cols + chunk_c - 1) // chunk_c) < 4 * threads:
+            chunk_c //= 2
+        t0 = time.perf_counter()
+        # the reference runs one goroutine per exponent (cmd/idw.go:153-161), each a full ChunkSolve
+        for p in exps:
+            O.chunk_solve_rows(ps, oi(xi), oi(yi), rows, cols, 0, nrows, 1, chunk_c, float(p), threads)
+        return time.perf_counter() - t0
+
+    t = run(1)  # calibrate on one row, then size the sample for ~`seconds`
+    nrows = int(max(1, min(rows, seconds / max(t, 1e-6))))
+    return dict(run=lambda: run(nrows), evals=float(nrows) * cols * n, E=E, threads=threads, nrows=nrows,
+                cols=cols, n=n, calib_s=t)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    s = cpu_sample(args.workload, args.cpu_seconds)
+    for _ in range(min(args.warmup, 1)):  # CPU code has no clocks to warm; one pass touches the pages
+        s["run"]()
+    t = 0.0
+    for _ in range(args.steps):
+        t += s["run"]()
+    val = s["evals"] * args.steps / t / 1e9
+    sample = (f"rows [0,{s['nrows']}) x {s['cols']} cols of {args.workload} x {s['n']} points x {s['E']} exponent(s), "
+              f"ChunkSolve semantics (1-row chunks over a {s['threads']}-thread pool), oracle port of the Go algorithm")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 0, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": _workload_name(args.workload, 1), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": s["threads"], "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
+def _workload_name(name, world):
+    from v2r_b200 import workloads
+    s = workloads.SPECS[name]
+    exps = []
+    e = s["es"]
+    while e < s["ee"]:
+        exps.append(e)
+        e += s["ei"]
+    band = f"{s['cells']}x{s['cells']}"
+    grid = band if world == 1 else f"{s['cells'] * world}x{s['cells']} ({world} row bands of {band})"
+    return f"{name}: {s['n']} {s['kind']} points -> {grid} grid, p={exps if len(exps) > 1 else exps[0]}"
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class Clocks:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import v2r_b200 as V
+    from v2r_b200 import _lib, workloads
+    from v2r_b200.idw import make_grid
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun so `python bench.py --gpus N` works by itself
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29517"] + sys.argv
+            return subprocess.call(cmd)
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: v2r_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.load()
+    prec = _lib.FP64 if args.precision == "fp64" else _lib.FP32
+
+    # ---- workload: every rank keeps one workload-sized row band (weak scaling) ----------------
+    x, y, w, xi, yi, exps = workloads.make(args.workload, scale_rows=world)
+    ps = V.MakeCoordSpace(x, y, w, xi, yi)
+    grid = make_grid(xi, yi)
+    band = grid.rows // world
+    row0 = rank * band
+    nrows = band if args.band_rows <= 0 else min(args.band_rows, band)
+    n, E = len(ps), len(exps)
+
+    # ---- inputs resident in HBM: rank 0 uploads, NCCL broadcast replicates (outside the timed region)
+    def dev_arr(a, dtype):
+        t = torch.empty(len(a), dtype=dtype, device=dev)
+        if rank == 0:
+            t.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        if world > 1:
+            dist.broadcast(t, 0)
+        return t
+    dx, dy, dw = dev_arr(ps.x, torch.float64), dev_arr(ps.y, torch.float64), dev_arr(ps.w, torch.float64)
+    dkr, dkc = dev_arr(ps.key_r, torch.int64), dev_arr(ps.key_c, torch.int64)
+    dout = torch.empty((E, nrows, grid.cols), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    exps_c = np.ascontiguousarray(exps, dtype=np.float64)
+
+    def step():
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(L.v2r_idw_launch_rows(local, C.c_void_p(stream), C.c_void_p(dx.data_ptr()), C.c_void_p(dy.data_ptr()),
+                                         C.c_void_p(dw.data_ptr()), C.c_void_p(dkr.data_ptr()), C.c_void_p(dkc.data_ptr()), n,
+                                         C.byref(grid), row0, nrows, C.c_void_p(exps_c.ctypes.data), E, prec,
+                                         C.c_void_p(dout.data_ptr())))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+        flush.zero_()
+    barrier()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = L.v2r_idw_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for a, b in evs:
+        a.record()
+        step()
+        b.record()
+        flush.zero_()  # L2 flush between timed iterations (outside the event pairs)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = L.v2r_idw_launch_count() - launches0
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    pair_evals_step = float(nrows) * grid.cols * n * world          # all ranks
+    value = pair_evals_step * args.steps / (ms_total * 1e-3) / 1e9
+
+    # sanity: the band is finite and exact-hit cells carry their weights (cheap, device side)
+    assert bool(torch.isfinite(dout).all().item()), "non-finite raster in the bench band"
+
+    # ---- e2e through the C ABI with host buffers ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, V, L, ps, grid, exps_c, prec, world, rank, local, barrier, band)
+
+    # ---- roofline + peaks + cpu baseline (rank 0) --------------------------------------------------
+    if rank == 0:
+        dfma, m64, m32, ffma = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        _lib.check(L.v2r_idw_measure_peaks(local, 60.0, C.byref(dfma), C.byref(m64), C.byref(m32), C.byref(ffma)))
+        buf = C.create_string_buffer(512)
+        ops = C.c_double()
+        _lib.check(L.v2r_idw_describe(C.c_void_p(exps_c.ctypes.data), E, prec, buf, 512, C.byref(ops)))
+        A = ALGO_SLOTS[args.workload]
+        per_gpu_pairs_s = value * 1e9 / world
+        achieved_tflops = per_gpu_pairs_s * 2 * A / 1e12
+        peak_tflops = 2 * dfma.value / 1e3
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(f"{args.workload}/{args.precision}")
+            except Exception:
+                traffic = None
+        roofline = {
+            "bound": "fp64-pipe", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": achieved_tflops / peak_tflops if peak_tflops else None, "traffic": traffic,
+            "peak_source": "in-run DFMA issue-rate microbenchmark (MEASURED_PEAKS.json has no FP64 entry)",
+            "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP64_TFLOPS,
+            "algorithmic_fp64_slots_per_pair": A, "issued_fp64_slots_per_pair_model": ops.value,
+            "fp64_pipe_busy_model": per_gpu_pairs_s * ops.value / (dfma.value * 1e9) if dfma.value else None,
+            "kernel": buf.value.decode(), "ms_per_launch": ms_total / args.steps,
+            "measured_peaks_ginst_s": {"dfma": dfma.value, "mufu_rcp64h": m64.value, "mufu_rcp_f32": m32.value, "ffma": ffma.value},
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            s = cpu_sample(args.workload, args.cpu_seconds)
+            tc = s["run"]()
+            cpu = {"value": s["evals"] / tc / 1e9, "unit": UNIT, "cores": s["threads"], "kind": "port",
+                   "sample": f"rows [0,{s['nrows']}) x {s['cols']} cols x {s['n']} points x {s['E']} exponent(s) of {args.workload}, "
+                             f"oracle port of ChunkSolve (1-row chunks), {tc:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if prec == _lib.FP64 else "f32(tile)/f64(accumulate)",
+            "data": "synthetic",
+            "config": {"workload": _workload_name(args.workload, world), "points_after_dedupe": n, "exponents": E,
+                       "rows_per_rank": nrows, "cols": int(grid.cols), "l2": "flushed between timed iterations (256 MiB memset); output band > L2",
+                       "parallelism": f"row bands x{world}"},
+            "pair_evals_per_step": pair_evals_step, "raster_evals_per_s_G": value * E,
+            "wall_s": t_wall, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, V, L, ps, grid, exps_c, prec, world, rank, local, barrier, band):
+    """The call a user of the library makes: v2r_idw_solve with host buffers.  At N > 1 rank 0 drives all
+    N GPUs through ONE context (v2r_idw_init(N): NCCL broadcast of the points, row bands, gather to
+    device 0, D2H) -- the shape the Go host uses; the other ranks idle at the barrier."""
+    import ctypes as C
+    from v2r_b200 import _lib
+    n, E = len(ps), len(exps_c)
+    res = None
+    barrier()
+    if rank == 0:
+        ctx = V.IdwContext(n_gpus=world) if world > 1 else V.IdwContext(device=local)
+        rows = grid.rows if args.band_rows <= 0 else min(args.band_rows * world, grid.rows)
+        nbytes_out = E * rows * grid.cols * 8
+        pin = C.c_void_p()
+        _lib.check(L.v2r_idw_alloc_pinned(nbytes_out, C.byref(pin)))
+        out = np.ctypeslib.as_array((C.c_double * (nbytes_out // 8)).from_address(pin.value))
+        # pinned inputs, as a reader filling v2r_idw_alloc_pinned buffers would leave them
+        pins = []
+        def pinned_copy(a):
+            p = C.c_void_p()
+            _lib.check(L.v2r_idw_alloc_pinned(a.nbytes, C.byref(p)))
+            pins.append(p)
+            v = np.ctypeslib.as_array((C.c_byte * a.nbytes).from_address(p.value)).view(a.dtype)
+            v[:] = a
+            return v
+        hx, hy, hw = pinned_copy(ps.x), pinned_copy(ps.y), pinned_copy(ps.w)
+        hkr, hkc = pinned_copy(ps.key_r), pinned_copy(ps.key_c)
+        hps = V.PointSet(hx, hy, hw, hkr, hkc)
+        out3 = out.reshape(E, rows, grid.cols)
+        times = []
+        for i in range(1 + max(1, args.e2e_steps)):
+            t0 = time.perf_counter()
+            ctx.solve_rows(hps, grid, 0, rows, exps_c, prec, out=out3)
+            times.append(time.perf_counter() - t0)
+        tm = ctx.last_timing()
+        t = sum(times[1:]) / len(times[1:])
+        res = {"value": float(rows) * grid.cols * n / t / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(n * 40),
+               "d2h_bytes_per_step": int(nbytes_out), "ms_per_step": t * 1e3, "steps": len(times) - 1,
+               "call": f"v2r_idw_solve_rows via v2r_idw_init({world}) with pinned host buffers",
+               "breakdown_ms": tm, "finite": bool(np.isfinite(out3[:, ::max(1, rows // 64)]).all())}
+        ctx.close()
+        for p in pins + [pin]:
+            L.v2r_idw_free_pinned(p)
+    barrier()
+    return res
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -334,6 +334,49 @@ int oracle_solve_rows(int64_t n, const double *x, const double *y, const double 
     return 0;
 }
 
+/* The same per-cell evaluation on an arbitrary list of cells (rr[i], cc[i]): lets the tests
+ * spot-check full-size rasters (BASELINE.json configs c2..c5) without running the whole grid on
+ * the CPU.  nthreads > 1 splits the list statically. */
+typedef struct {
+    const keymap *m; int64_t n; const double *x, *y, *w; double x_min, x_step, y_min, y_step, exp;
+    const int64_t *rr, *cc; int64_t lo, hi; double *out;
+} cells_job;
+
+static void *cells_worker(void *arg)
+{
+    cells_job *j = (cells_job *)arg;
+    for (int64_t i = j->lo; i < j->hi; i++)
+        j->out[i] = cell_idw(j->m, j->n, j->x, j->y, j->w, j->x_min, j->x_step, j->y_min, j->y_step, j->exp,
+                             j->rr[i], j->cc[i]);
+    return NULL;
+}
+
+int oracle_solve_cells(int64_t n, const double *x, const double *y, const double *w,
+                       const int64_t *kr, const int64_t *kc, double x_min, double x_step,
+                       double y_min, double y_step, int64_t ncells, const int64_t *rr,
+                       const int64_t *cc, double exp, int nthreads, double *out)
+{
+    keymap m;
+    if (build_keymap(&m, n, kr, kc) != 0) return -1;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    cells_job jobs[256];
+    pthread_t th[256];
+    int started = 0;
+    for (int t = 0; t < nthreads; t++) {
+        cells_job j = {&m, n, x, y, w, x_min, x_step, y_min, y_step, exp, rr, cc,
+                       ncells * t / nthreads, ncells * (t + 1) / nthreads, out};
+        jobs[t] = j;
+    }
+    for (int t = 1; t < nthreads; t++)
+        if (pthread_create(&th[started], NULL, cells_worker, &jobs[t]) == 0) started++;
+        else cells_worker(&jobs[t]);
+    cells_worker(&jobs[0]);
+    for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+    keymap_free(&m);
+    return 0;
+}
+
 int oracle_full_solve(int64_t n, const double *x, const double *y, const double *w,
                       const int64_t *kr, const int64_t *kc, double x_min, double x_step,
                       double y_min, double y_step, int64_t rows, int64_t cols, double exp, double *out)

@@ -67,6 +67,8 @@ def lib():
         L.oracle_chunk_solve_rows.argtypes = pts + geo + [C.c_int64] * 6 + [C.c_double, C.c_int, _D]
         L.oracle_full_solve_ld.restype = C.c_int
         L.oracle_full_solve_ld.argtypes = pts + geo + [C.c_int64, C.c_int64, C.c_double, _D, _D]
+        L.oracle_solve_cells.restype = C.c_int
+        L.oracle_solve_cells.argtypes = pts + geo + [C.c_int64, _I, _I, C.c_double, C.c_int, _D]
         L.oracle_exp_range.restype = C.c_int64
         L.oracle_exp_range.argtypes = [C.c_double] * 3 + [_D, C.c_int64]
         L.oracle_num_threads.restype = C.c_int
@@ -184,6 +186,16 @@ def chunk_solve_rows(ps: PointSet, xinfo: Info, yinfo: Info, rows: int, cols: in
     keep, a = _args(ps, xinfo, yinfo)
     rc = lib().oracle_chunk_solve_rows(*a, rows, cols, row0, nrows, chunk_r, chunk_c, exp, nthreads, _d(out))
     assert rc == 0, rc
+    return out
+
+
+def solve_cells(ps: PointSet, xinfo: Info, yinfo: Info, exp: float, rr, cc, nthreads: int = 0):
+    """calculateIDW on a list of cells (for spot checks of full-size rasters)."""
+    rr, cc = _i64(rr), _i64(cc)
+    out = np.empty(len(rr))
+    keep, a = _args(ps, xinfo, yinfo)
+    rc = lib().oracle_solve_cells(*a, len(rr), _i(rr), _i(cc), exp, nthreads or num_threads(), _d(out))
+    assert rc == 0
     return out
 
 

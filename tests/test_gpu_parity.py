@@ -1,0 +1,283 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, the reference's golden rasters
+and size-independent properties.  Runs on a B200 only (`-m gpu`).
+
+Tolerance (SURVEY.md section 8c, FP64 bar of north_star = 1e-12 relative):
+    |z_gpu - z_ref| <= 1e-12 * max(|z_ref|, sum|w_i| h_i / sum h_i)
+NaN positions must match exactly; exact-hit cells must be bit-equal to the stored weight.
+"""
+import os
+import queue
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402  (checker only)
+
+import v2r_b200 as V  # noqa: E402
+from v2r_b200 import _lib, raster_io, read_data, workloads  # noqa: E402
+from v2r_b200.idw import make_grid  # noqa: E402
+
+REL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = V.IdwContext(1)
+    yield c
+    c.close()
+
+
+def o_info(i):
+    return O.Info(i.min, i.max, i.step)
+
+
+def o_ps(ps):
+    return O.PointSet(ps.x, ps.y, ps.w, ps.key_r, ps.key_c)
+
+
+def assert_parity(z, z_ref, scale, rel=REL, what=""):
+    z, z_ref, scale = np.asarray(z), np.asarray(z_ref), np.asarray(scale)
+    assert z.shape == z_ref.shape
+    assert np.array_equal(np.isnan(z), np.isnan(z_ref)), f"{what}: NaN positions differ"
+    ok = ~np.isnan(z_ref)
+    err = np.abs(z[ok] - z_ref[ok]) / np.maximum(np.maximum(np.abs(z_ref[ok]), scale[ok]), 1e-300)
+    assert err.size == 0 or err.max() <= rel, f"{what}: max scaled error {err.max():.3e} > {rel:g}"
+    return float(err.max()) if err.size else 0.0
+
+
+def random_case(seed, n, rows, cols, step=1.0, x0=0.0, y0=0.0, signed=True):
+    rng = np.random.default_rng(seed)
+    xi = V.Info(x0, x0 + cols * step - 1, step)
+    yi = V.Info(y0, y0 + rows * step - 1, step)
+    x = rng.uniform(xi.min, xi.min + cols * step, n)
+    y = rng.uniform(yi.min, yi.min + rows * step, n)
+    w = rng.uniform(-100, 100, n) if signed else rng.uniform(0, 500, n)
+    ps = V.MakeCoordSpace(x, y, w, xi, yi)
+    return ps, xi, yi
+
+
+def load_golden(golden_dir):
+    x, y, w, proj, xi, yi = read_data.ReadTextData(os.path.join(golden_dir, "idw_in.txt"), 2284)
+    return V.MakeCoordSpace(x, y, w, xi, yi), xi, yi, proj
+
+
+# --------------------------------------------------------------------------- reference goldens
+@pytest.mark.parametrize("cs", ["Serial", "Conc"])
+def test_golden_step1_through_gpu_path(golden_dir, tmp_path, ctx, cs):
+    """features/idw/idw_test.go:14-76 replayed: FullSolve / ChunkSolve(3,2) at pow 1.7 -> tiff ->
+    Int16 AAIGrid -> byte compare with idw_correct_step1-1.asc."""
+    data, xi, yi, proj = load_golden(golden_dir)
+    outfile = str(tmp_path / f"idw_step1-1pow1.7{'chunked' if cs == 'Conc' else ''}")
+    channel = queue.Queue()
+    if cs == "Conc":
+        V.ChunkSolve(data, outfile + ".tiff", xi, yi, 3, 2, proj, 1.7, channel, ctx=ctx)
+    else:
+        V.FullSolve(data, outfile + ".tiff", xi, yi, proj, 1.7, channel, ctx=ctx)
+    assert "completed in" in channel.get_nowait()
+    raster_io.TransferType(outfile + ".tiff", outfile + ".asc", "Int16")
+    assert raster_io.SameFiles(outfile + ".asc", os.path.join(golden_dir, "idw_correct_step1-1.asc"))
+
+
+def test_golden_step2_stale_keys_through_gpu_path(golden_dir, tmp_path, ctx):
+    """idw_correct_step2-2.asc: step-2 grid, keys made at step 1 (exact hit = key table, not geometry)."""
+    data, xi, yi, proj = load_golden(golden_dir)
+    x2, y2 = V.Info(xi.min, xi.max, 2.0), V.Info(yi.min, yi.max, 2.0)
+    out = str(tmp_path / "s2")
+    V.FullSolve(data, out + ".tiff", x2, y2, proj, 1.7, None, ctx=ctx)
+    raster_io.TransferType(out + ".tiff", out + ".asc", "Int16")
+    assert raster_io.SameFiles(out + ".asc", os.path.join(golden_dir, "idw_correct_step2-2.asc"))
+
+
+@pytest.mark.parametrize("p", [1.7, 0.5, 2.0, 1.0, 3.0, 1.5, 0.3, 4.5, 6.0])
+def test_c1_vs_oracle_and_truth(golden_dir, ctx, p):
+    data, xi, yi, _ = load_golden(golden_dir)
+    z = V.solve(data, xi, yi, [p], ctx=ctx)[0]
+    ref = O.full_solve(o_ps(data), o_info(xi), o_info(yi), p)
+    truth, scale = O.full_solve_truth(o_ps(data), o_info(xi), o_info(yi), p)
+    assert_parity(z, ref, scale, what=f"c1 p={p} vs oracle")
+    assert_parity(z, truth, scale, what=f"c1 p={p} vs long-double truth")
+    for r, c, w in zip(data.key_r, data.key_c, data.w):
+        assert z[r, c] == w  # exact hit: bit-equal
+
+
+# --------------------------------------------------------------------------- random cases
+CLASSES = [2.0, 4.0, 1.0, 3.0, 5.0, 0.5, 1.5, 2.5, 1.7, 0.3, 0.30000000000000004, 7.25, 0.0, -1.0, -2.0]
+
+
+@pytest.mark.parametrize("p", CLASSES)
+def test_random_1k_points_256_grid(ctx, p):
+    ps, xi, yi = random_case(11, 1000, 256, 256, step=3.0, x0=-50.0, y0=1e4)
+    z = V.solve(ps, xi, yi, [p], ctx=ctx)[0]
+    ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), p)
+    _, scale = O.full_solve_truth(o_ps(ps), o_info(xi), o_info(yi), p)
+    assert_parity(z, ref, scale, what=f"p={p}")
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 511, 512, 513, 1024, 1025, 1537])
+def test_tile_boundaries_and_ragged_grids(ctx, n):
+    """point counts around the 512-point TMA tile, grid sizes that are not multiples of the CTA tile"""
+    ps, xi, yi = random_case(100 + n, n, 37, 131, step=0.7)
+    for p in (2.0, 1.5, 1.7):
+        z = V.solve(ps, xi, yi, [p], ctx=ctx)[0]
+        ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), p)
+        _, scale = O.full_solve_truth(o_ps(ps), o_info(xi), o_info(yi), p)
+        assert_parity(z, ref, scale, what=f"n={n} p={p}")
+
+
+def test_sweeps_match_single_exponent_solves(ctx):
+    ps, xi, yi = random_case(5, 700, 96, 160, step=2.0)
+    for exps in (V.exp_range(0.5, 5.0, 0.5), V.exp_range(1.0, 3.0, 0.5), V.exp_range(2.0, 9.0, 2.0),
+                 V.exp_range(1.0, 5.0, 1.0), V.exp_range(0.1, 0.75, 0.1), np.array([3.0, 1.0, 2.0]),
+                 V.exp_range(0.5, 7.5, 0.5), V.exp_range(1.1, 3.4, 0.2)):
+        zs = V.solve(ps, xi, yi, exps, ctx=ctx)
+        assert zs.shape == (len(exps), 96, 160)
+        for e, p in enumerate(exps):
+            ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), float(p))
+            _, scale = O.full_solve_truth(o_ps(ps), o_info(xi), o_info(yi), float(p))
+            assert_parity(zs[e], ref, scale, what=f"sweep {exps} e={e}")
+
+
+def test_edge_semantics_match_reference(ctx):
+    xi, yi = V.Info(0, 3, 1), V.Info(0, 3, 1)
+    # stale key: the point sits on node (1,1) but is keyed outside the grid -> geometric d = 0 -> NaN
+    ps = V.PointSet(np.array([1.0, 3.0]), np.array([1.0, 2.0]), np.array([5.0, 9.0]),
+                    np.array([7, 2], np.int64), np.array([7, 3], np.int64))
+    for p in (2.0, 1.0, 0.5, 1.7):
+        z = V.solve(ps, xi, yi, [p], rows=4, cols=4, ctx=ctx)[0]
+        ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), p, 4, 4)
+        assert np.isnan(z[1, 1]) and np.isnan(z).sum() == 1 and z[2, 3] == 9.0
+        assert np.array_equal(np.isnan(z), np.isnan(ref))
+    z0 = V.solve(ps, xi, yi, [0.0], rows=4, cols=4, ctx=ctx)[0]      # p = 0: plain mean, even at d = 0
+    assert z0[1, 1] == 7.0 and z0[0, 0] == 7.0 and z0[2, 3] == 9.0
+    zn = V.solve(ps, xi, yi, [-1.0], rows=4, cols=4, ctx=ctx)[0]     # p < 0: d = 0 -> h = 0
+    refn = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), -1.0, 4, 4)
+    assert zn[1, 1] == 9.0 and np.allclose(zn, refn, rtol=1e-13)
+    empty = V.PointSet(*(np.empty(0) for _ in range(3)), np.empty(0, np.int64), np.empty(0, np.int64))
+    assert np.isnan(V.solve(empty, xi, yi, [2.0], rows=4, cols=4, ctx=ctx)).all()  # N = 0 -> 0/0
+
+
+def test_points_left_of_origin_and_negative_keys(ctx):
+    xi, yi = V.Info(0, 20, 1), V.Info(0, 20, 1)
+    x = np.array([-0.5, 3.2, -7.0, 25.0])
+    y = np.array([0.2, -0.9, 4.0, 30.0])
+    w = np.array([1.0, 2.0, 3.0, 4.0])
+    ps = V.MakeCoordSpace(x, y, w, xi, yi)
+    ops = O.make_coord_space(x, y, w, o_info(xi), o_info(yi))
+    assert ps.key_r.tolist() == ops.key_r.tolist() and ps.key_c.tolist() == ops.key_c.tolist()
+    z = V.solve(ps, xi, yi, [2.0], ctx=ctx)[0]
+    ref = O.full_solve(ops, o_info(xi), o_info(yi), 2.0)
+    _, scale = O.full_solve_truth(ops, o_info(xi), o_info(yi), 2.0)
+    assert_parity(z, ref, scale)
+    assert z[0, 0] == 1.0 and z[0, 3] == 2.0     # truncation toward zero pulls them into row/col 0
+
+
+def test_row_bands_and_stream_equal_full(ctx):
+    ps, xi, yi = random_case(21, 900, 150, 70, step=5.0)
+    grid = make_grid(xi, yi)
+    exps = [1.0, 1.5, 2.0]
+    full = ctx.solve(ps, grid, exps)
+    parts = np.concatenate([ctx.solve_rows(ps, grid, r0, min(40, grid.rows - r0), exps) for r0 in range(0, grid.rows, 40)], axis=1)
+    assert np.array_equal(full, parts)
+    seen = np.full_like(full, np.nan)
+    for r0, band in ctx.stream(ps, grid, exps, band_rows=33):
+        seen[:, r0:r0 + band.shape[1]] = band
+    assert np.array_equal(full, seen)
+    t = ctx.last_timing()
+    assert t["kernel_ms"] > 0
+
+
+def test_epsg2284_magnitudes(ctx):
+    """coordinates ~1.2e7 ft like the gpkg fixture (tools/processing/gpkg_test.go:14-27)"""
+    ps, xi, yi = random_case(31, 800, 120, 120, step=100.0, x0=1.2020401943588393e+07, y0=3.885548111378168e+06, signed=False)
+    for p in (2.0, 1.5):
+        z = V.solve(ps, xi, yi, [p], ctx=ctx)[0]
+        ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), p)
+        _, scale = O.full_solve_truth(o_ps(ps), o_info(xi), o_info(yi), p)
+        assert_parity(z, ref, scale, what=f"epsg2284 p={p}")
+
+
+def test_gpkg_fixture_end_to_end(golden_dir, ctx):
+    x, y, w, proj, xi, yi = read_data.ReadGeoPackage(os.path.join(golden_dir, "input.gpkg"), "wsels", "elevation", 500.0, 500.0)
+    assert len(x) == 14 and proj.startswith("PROJCS[")
+    ps = V.MakeCoordSpace(x, y, w, xi, yi)
+    z = V.solve(ps, xi, yi, [1.5, 2.0], ctx=ctx)
+    for e, p in enumerate((1.5, 2.0)):
+        ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), p)
+        _, scale = O.full_solve_truth(o_ps(ps), o_info(xi), o_info(yi), p)
+        assert_parity(z[e], ref, scale, what=f"gpkg p={p}")
+
+
+def test_error_behaviour(ctx):
+    ps, xi, yi = random_case(1, 10, 8, 8)
+    grid = make_grid(xi, yi)
+    with pytest.raises(_lib.IdwError) as e:
+        ctx.solve(ps, grid, [float("nan")])
+    assert e.value.code == _lib.EINVAL
+    with pytest.raises(_lib.IdwError):
+        ctx.solve_rows(ps, grid, 4, 10, [2.0], out=np.empty((1, 10, 8)))   # rows outside the grid
+    with pytest.raises(_lib.IdwError):
+        ctx.solve(ps, grid, np.ones(65))                                     # too many exponents
+    with pytest.raises(ValueError):
+        V.FullSolve(ps, "out.png", xi, yi, "", 2.0, ctx=ctx)                # idw.go:19-25 suffix check
+    with pytest.raises(_lib.IdwError):
+        V.exp_range(1.0, 1.0, 0.5)                                          # cmd/idw.go:86-88
+    with pytest.raises(_lib.IdwError):
+        V.exp_range(1.0, 2.0, 0.0)                                          # cmd/idw.go:83-85
+
+
+# --------------------------------------------------------------------------- full-size properties
+@pytest.fixture(scope="module")
+def c2():
+    x, y, w, xi, yi, exps = workloads.make("c2")
+    return V.MakeCoordSpace(x, y, w, xi, yi), xi, yi, exps
+
+
+def test_c2_full_size_spot_check_and_properties(ctx, c2):
+    """BASELINE.json config 2 (100 k points -> 4096^2, p = 2) at full size:
+    (a) 400 random cells + every 997th exact-hit cell against the oracle,
+    (b) constant weights reproduce the constant, (c) linearity in the weights,
+    (d) row bands computed separately are bit-identical to the full raster."""
+    ps, xi, yi, exps = c2
+    grid = make_grid(xi, yi)
+    assert (grid.rows, grid.cols) == (4096, 4096)
+    z = ctx.solve(ps, grid, exps)[0]
+    assert not np.isnan(z).any()
+    rng = np.random.default_rng(3)
+    rr = np.concatenate([rng.integers(0, grid.rows, 400), ps.key_r[::997]])
+    cc = np.concatenate([rng.integers(0, grid.cols, 400), ps.key_c[::997]])
+    ref = O.solve_cells(o_ps(ps), o_info(xi), o_info(yi), 2.0, rr, cc)
+    ops_abs = O.PointSet(ps.x, ps.y, np.abs(ps.w), ps.key_r, ps.key_c)
+    scale = O.solve_cells(ops_abs, o_info(xi), o_info(yi), 2.0, rr, cc)
+    assert_parity(z[rr, cc], ref, scale, what="c2 spot check")
+    assert np.array_equal(z[ps.key_r, ps.key_c], ps.w)           # all 99.7 k exact-hit cells bit-equal
+    # (b) constant field
+    const = V.PointSet(ps.x, ps.y, np.full(len(ps), 123.456), ps.key_r, ps.key_c)
+    zc = ctx.solve_rows(const, grid, 1000, 64, exps)[0]
+    assert np.max(np.abs(zc / 123.456 - 1)) < 1e-13
+    # (c) linearity: z(2 w1 - 3 w2) = 2 z(w1) - 3 z(w2) within the tolerance of the combined magnitudes
+    w2 = np.random.default_rng(4).uniform(0, 500, len(ps))
+    band = (2048, 32)
+    z1 = ctx.solve_rows(ps, grid, *band, exps)[0]
+    z2 = ctx.solve_rows(V.PointSet(ps.x, ps.y, w2, ps.key_r, ps.key_c), grid, *band, exps)[0]
+    z3 = ctx.solve_rows(V.PointSet(ps.x, ps.y, 2 * ps.w - 3 * w2, ps.key_r, ps.key_c), grid, *band, exps)[0]
+    assert np.max(np.abs(z3 - (2 * z1 - 3 * z2))) <= 1e-12 * 2500
+    # (d) bands
+    assert np.array_equal(z[2048:2080], z1)
+
+
+def test_c3_sweep_full_width_band(ctx):
+    """BASELINE.json config 3 (250 k points -> 8192^2, p = 0.5..4.5, one pass): one 32-row band of the
+    full-width grid against the oracle on sampled cells, all nine exponents."""
+    x, y, w, xi, yi, exps = workloads.make("c3")
+    ps = V.MakeCoordSpace(x, y, w, xi, yi)
+    grid = make_grid(xi, yi)
+    assert (grid.rows, grid.cols, len(exps)) == (8192, 8192, 9)
+    r0 = 4096
+    z = ctx.solve_rows(ps, grid, r0, 32, exps)
+    rng = np.random.default_rng(5)
+    rr, cc = r0 + rng.integers(0, 32, 40), rng.integers(0, grid.cols, 40)
+    for e, p in enumerate(exps):
+        ref = O.solve_cells(o_ps(ps), o_info(xi), o_info(yi), float(p), rr, cc)
+        assert_parity(z[e][rr - r0, cc], ref, np.abs(ref), what=f"c3 p={p}")   # w >= 0 so scale == |z|

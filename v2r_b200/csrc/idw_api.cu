@@ -1,0 +1,663 @@
+// idw_api.cu -- host side of libv2r_idw.so: contexts, host helpers that define the inputs of the
+// hot path, and the host-buffer solve entry points (single process driving 1..8 GPUs).
+// See include/v2r_idw.h for the contract of every function.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include <nccl.h>  // types and prototypes only; the library is dlopen'ed when n_gpus > 1
+
+#include "idw_internal.h"
+
+namespace v2r {
+
+// ------------------------------------------------------------------------------------------
+// error reporting: thread-local message, integer status across the ABI
+// ------------------------------------------------------------------------------------------
+static thread_local char t_err[512] = "";
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof t_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+const char *last_error() { return t_err; }
+
+#define CUDA_TRY(expr)                                                                                \
+    do {                                                                                              \
+        cudaError_t ce__ = (expr);                                                                    \
+        if (ce__ != cudaSuccess) {                                                                    \
+            cudaGetLastError();                                                                       \
+            return set_error(ce__ == cudaErrorMemoryAllocation ? V2R_IDW_ENOMEM : V2R_IDW_ECUDA,      \
+                             "%s: %s", #expr, cudaGetErrorString(ce__));                              \
+        }                                                                                             \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// NCCL, loaded lazily (single-GPU contexts never touch it)
+// ------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+
+static int load_nccl() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.handle) return V2R_IDW_OK;
+    const char *names[] = {getenv("V2R_IDW_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names) {
+        if (!nm || !*nm) continue;
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return set_error(V2R_IDW_ENCCL, "cannot load NCCL (libnccl.so.2): %s", dlerror());
+#define LOAD(sym)                                                                      \
+    g_nccl.sym = reinterpret_cast<decltype(g_nccl.sym)>(dlsym(h, "nccl" #sym));        \
+    if (!g_nccl.sym) return set_error(V2R_IDW_ENCCL, "NCCL symbol nccl" #sym " missing")
+    LOAD(CommInitAll);
+    LOAD(CommDestroy);
+    LOAD(GroupStart);
+    LOAD(GroupEnd);
+    LOAD(Broadcast);
+    LOAD(Send);
+    LOAD(Recv);
+    LOAD(GetErrorString);
+#undef LOAD
+    g_nccl.handle = h;
+    return V2R_IDW_OK;
+}
+
+#define NCCL_TRY(expr)                                                                            \
+    do {                                                                                          \
+        ncclResult_t nr__ = (expr);                                                               \
+        if (nr__ != ncclSuccess)                                                                  \
+            return set_error(V2R_IDW_ENCCL, "%s: %s", #expr, g_nccl.GetErrorString(nr__));        \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct DeviceState {
+    int device = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    double *d_x = nullptr, *d_y = nullptr, *d_z = nullptr;
+    long long *d_kr = nullptr, *d_kc = nullptr;
+    size_t pts_cap = 0;  // points
+    double *d_band[2] = {nullptr, nullptr};
+    size_t band_cap[2] = {0, 0};  // doubles
+    cudaEvent_t k_start[2] = {nullptr, nullptr}, k_stop[2] = {nullptr, nullptr};
+    cudaEvent_t c_start = nullptr, c_stop = nullptr, up_start = nullptr, up_stop = nullptr;
+    ncclComm_t comm = nullptr;
+    long long band_row0 = 0, band_rows = 0;  // rows owned in the current session
+    double kernel_ms = 0;
+};
+
+struct Session {
+    bool active = false;
+    v2r_idw_grid grid{};
+    long long row0 = 0, nrows = 0;  // requested row range
+    std::vector<double> exps;
+    int precision = 0;
+    long long sub_rows = 0;   // rows per device per round
+    long long rounds = 0;
+    long long cur_round = 0;
+    int cur_dev = 0;
+    long long n = 0;
+};
+
+}  // namespace v2r
+
+struct v2r_idw_ctx {
+    std::mutex mu;
+    std::vector<v2r::DeviceState> dev;
+    double *d_gather = nullptr;  // on device 0: landing buffer for peer bands
+    size_t gather_cap = 0;
+    v2r::Session ses;
+    double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0;
+};
+
+namespace v2r {
+
+static void free_device_state(DeviceState &d) {
+    cudaSetDevice(d.device);
+    if (d.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d.comm);
+    for (void *p : {(void *)d.d_x, (void *)d.d_y, (void *)d.d_z, (void *)d.d_kr, (void *)d.d_kc, (void *)d.d_band[0], (void *)d.d_band[1]})
+        if (p) cudaFree(p);
+    for (cudaEvent_t e : {d.k_start[0], d.k_start[1], d.k_stop[0], d.k_stop[1], d.c_start, d.c_stop, d.up_start, d.up_stop})
+        if (e) cudaEventDestroy(e);
+    if (d.compute) cudaStreamDestroy(d.compute);
+    if (d.copy) cudaStreamDestroy(d.copy);
+}
+
+static int init_device_state(DeviceState &d, int device) {
+    d.device = device;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d.compute, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreate(&d.k_start[i]));
+        CUDA_TRY(cudaEventCreate(&d.k_stop[i]));
+    }
+    CUDA_TRY(cudaEventCreate(&d.c_start));
+    CUDA_TRY(cudaEventCreate(&d.c_stop));
+    CUDA_TRY(cudaEventCreate(&d.up_start));
+    CUDA_TRY(cudaEventCreate(&d.up_stop));
+    return V2R_IDW_OK;
+}
+
+static int create_ctx(const std::vector<int> &devices, v2r_idw_ctx **out) {
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return set_error(V2R_IDW_ECUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                         ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+    }
+    for (int dv : devices)
+        if (dv < 0 || dv >= count) return set_error(V2R_IDW_EINVAL, "device %d not present (%d visible)", dv, count);
+    auto *ctx = new (std::nothrow) v2r_idw_ctx();
+    if (!ctx) return set_error(V2R_IDW_ENOMEM, "out of host memory");
+    ctx->dev.resize(devices.size());
+    for (size_t i = 0; i < devices.size(); ++i) {
+        int rc = init_device_state(ctx->dev[i], devices[i]);
+        if (rc) {
+            for (auto &d : ctx->dev) free_device_state(d);
+            delete ctx;
+            return rc;
+        }
+    }
+    if (devices.size() > 1) {
+        int rc = load_nccl();
+        if (rc == V2R_IDW_OK) {
+            std::vector<ncclComm_t> comms(devices.size());
+            ncclResult_t nr = g_nccl.CommInitAll(comms.data(), (int)devices.size(), devices.data());
+            if (nr != ncclSuccess) rc = set_error(V2R_IDW_ENCCL, "ncclCommInitAll: %s", g_nccl.GetErrorString(nr));
+            else
+                for (size_t i = 0; i < devices.size(); ++i) ctx->dev[i].comm = comms[i];
+        }
+        if (rc) {
+            for (auto &d : ctx->dev) free_device_state(d);
+            delete ctx;
+            return rc;
+        }
+    }
+    *out = ctx;
+    return V2R_IDW_OK;
+}
+
+template <typename T>
+static int ensure(T *&p, size_t &cap, size_t need) {
+    if (need <= cap && p) return V2R_IDW_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t alloc = need + (need >> 3) + 64;
+    cudaError_t ce = cudaMalloc((void **)&p, alloc * sizeof(T));
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(V2R_IDW_ENOMEM, "cudaMalloc(%zu bytes): %s", alloc * sizeof(T), cudaGetErrorString(ce));
+    }
+    cap = alloc;
+    return V2R_IDW_OK;
+}
+
+static int ensure_points(DeviceState &d, size_t n) {
+    if (n <= d.pts_cap && d.d_x) return V2R_IDW_OK;
+    CUDA_TRY(cudaSetDevice(d.device));
+    for (void *p : {(void *)d.d_x, (void *)d.d_y, (void *)d.d_z, (void *)d.d_kr, (void *)d.d_kc})
+        if (p) cudaFree(p);
+    d.d_x = d.d_y = d.d_z = nullptr;
+    d.d_kr = d.d_kc = nullptr;
+    d.pts_cap = 0;
+    size_t cap = ((n + (n >> 3) + 1023) / 1024) * 1024;
+    CUDA_TRY(cudaMalloc((void **)&d.d_x, cap * 8));
+    CUDA_TRY(cudaMalloc((void **)&d.d_y, cap * 8));
+    CUDA_TRY(cudaMalloc((void **)&d.d_z, cap * 8));
+    CUDA_TRY(cudaMalloc((void **)&d.d_kr, cap * 8));
+    CUDA_TRY(cudaMalloc((void **)&d.d_kc, cap * 8));
+    d.pts_cap = cap;
+    return V2R_IDW_OK;
+}
+
+// Upload points to device 0 and replicate them to every other device with ONE grouped NCCL
+// broadcast per array over NVLink (north_star: "the point set is replicated with one NCCL broadcast").
+static int upload_points(v2r_idw_ctx *ctx, const double *x, const double *y, const double *z, const int64_t *kr,
+                         const int64_t *kc, long long n) {
+    for (auto &d : ctx->dev) {
+        int rc = ensure_points(d, (size_t)std::max<long long>(n, 1));
+        if (rc) return rc;
+    }
+    DeviceState &d0 = ctx->dev[0];
+    CUDA_TRY(cudaSetDevice(d0.device));
+    CUDA_TRY(cudaEventRecord(d0.up_start, d0.compute));
+    if (n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(d0.d_x, x, n * 8, cudaMemcpyHostToDevice, d0.compute));
+        CUDA_TRY(cudaMemcpyAsync(d0.d_y, y, n * 8, cudaMemcpyHostToDevice, d0.compute));
+        CUDA_TRY(cudaMemcpyAsync(d0.d_z, z, n * 8, cudaMemcpyHostToDevice, d0.compute));
+        CUDA_TRY(cudaMemcpyAsync(d0.d_kr, kr, n * 8, cudaMemcpyHostToDevice, d0.compute));
+        CUDA_TRY(cudaMemcpyAsync(d0.d_kc, kc, n * 8, cudaMemcpyHostToDevice, d0.compute));
+    }
+    if (ctx->dev.size() > 1 && n > 0) {
+        for (int a = 0; a < 5; ++a) {
+            NCCL_TRY(g_nccl.GroupStart());
+            for (auto &d : ctx->dev) {
+                void *src = a == 0 ? (void *)d0.d_x : a == 1 ? (void *)d0.d_y : a == 2 ? (void *)d0.d_z : a == 3 ? (void *)d0.d_kr : (void *)d0.d_kc;
+                void *dst = a == 0 ? (void *)d.d_x : a == 1 ? (void *)d.d_y : a == 2 ? (void *)d.d_z : a == 3 ? (void *)d.d_kr : (void *)d.d_kc;
+                // root's sendbuff is its own array; non-roots pass their receive buffer for both
+                NCCL_TRY(g_nccl.Broadcast(&d == &d0 ? src : dst, dst, (size_t)n, a < 3 ? ncclDouble : ncclInt64, 0, d.comm, d.compute));
+            }
+            NCCL_TRY(g_nccl.GroupEnd());
+        }
+    }
+    CUDA_TRY(cudaSetDevice(d0.device));
+    CUDA_TRY(cudaEventRecord(d0.up_stop, d0.compute));
+    return V2R_IDW_OK;
+}
+
+static long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
+
+// rows of device g's sub-band in round k, clipped to its band
+static void sub_band(const Session &s, const DeviceState &d, long long k, long long *r0, long long *nr) {
+    long long a = d.band_row0 + k * s.sub_rows;
+    long long e = std::min(a + s.sub_rows, d.band_row0 + d.band_rows);
+    *r0 = a;
+    *nr = e > a ? e - a : 0;
+}
+
+static int launch_round(v2r_idw_ctx *ctx, long long k) {
+    Session &s = ctx->ses;
+    const int buf = (int)(k & 1);
+    for (auto &d : ctx->dev) {
+        long long r0, nr;
+        sub_band(s, d, k, &r0, &nr);
+        if (nr <= 0) continue;
+        CUDA_TRY(cudaSetDevice(d.device));
+        CUDA_TRY(cudaEventRecord(d.k_start[buf], d.compute));
+        int rc;
+        if (s.precision == V2R_IDW_FP32)
+            rc = launch_rows_fp32(d.compute, d.d_x, d.d_y, d.d_z, d.d_kr, d.d_kc, s.n, s.grid, r0, nr, s.exps.data(), (int)s.exps.size(), d.d_band[buf]);
+        else
+            rc = launch_rows_fp64(d.compute, d.d_x, d.d_y, d.d_z, d.d_kr, d.d_kc, s.n, s.grid, r0, nr, s.exps.data(), (int)s.exps.size(), d.d_band[buf]);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(d.k_stop[buf], d.compute));
+    }
+    return V2R_IDW_OK;
+}
+
+static int begin_session(v2r_idw_ctx *ctx, const double *x, const double *y, const double *z, const int64_t *kr,
+                         const int64_t *kc, long long n, const v2r_idw_grid *grid, long long row0, long long nrows,
+                         const double *exps, int n_exps, int precision, long long band_rows) {
+    if (ctx->ses.active) return set_error(V2R_IDW_ESTATE, "a streaming session is already open on this context");
+    int rc = validate_launch((const void *)16, (const void *)16, (const void *)16, n, grid, row0, nrows, n_exps, (const void *)16);
+    if (rc) return rc;
+    if (n > 0 && (!x || !y || !z || !kr || !kc)) return set_error(V2R_IDW_EINVAL, "point or key arrays are NULL");
+    if (precision != V2R_IDW_FP64 && precision != V2R_IDW_FP32) return set_error(V2R_IDW_EINVAL, "unknown precision %d", precision);
+    std::vector<Pass> passes;
+    if ((rc = plan_sweep(exps, n_exps, passes))) return rc;
+
+    Session &s = ctx->ses;
+    s = Session{};
+    s.grid = *grid;
+    s.row0 = row0;
+    s.nrows = nrows;
+    s.exps.assign(exps, exps + n_exps);
+    s.precision = precision;
+    s.n = n;
+    ctx->h2d_ms = ctx->kernel_ms = ctx->d2h_ms = 0;
+
+    const long long G = (long long)ctx->dev.size();
+    // contiguous row band per device, multiple of 32 rows so CTA tiles stay whole
+    long long per = ceil_div(nrows, G);
+    per = ceil_div(per, 32) * 32;
+    for (long long g = 0; g < G; ++g) {
+        DeviceState &d = ctx->dev[g];
+        long long a = std::min(row0 + g * per, row0 + nrows), e = std::min(a + per, row0 + nrows);
+        d.band_row0 = a;
+        d.band_rows = e - a;
+        d.kernel_ms = 0;
+    }
+    // rows per device per round: keep one round of one device under ~1 GiB of output
+    const long long row_bytes = std::max<long long>(1, grid->cols) * 8 * n_exps;
+    long long sub = band_rows > 0 ? band_rows : std::max<long long>(32, ((1LL << 30) / row_bytes) / 32 * 32);
+    sub = std::min(sub, std::max<long long>(per, 1));
+    s.sub_rows = std::max<long long>(sub, 1);
+    s.rounds = per > 0 ? ceil_div(per, s.sub_rows) : 0;
+
+    const size_t band_doubles = (size_t)s.sub_rows * (size_t)std::max<long long>(grid->cols, 1) * (size_t)n_exps;
+    for (auto &d : ctx->dev) {
+        CUDA_TRY(cudaSetDevice(d.device));
+        for (int i = 0; i < 2; ++i)
+            if ((rc = ensure(d.d_band[i], d.band_cap[i], band_doubles))) return rc;
+    }
+    if (G > 1) {
+        CUDA_TRY(cudaSetDevice(ctx->dev[0].device));
+        if ((rc = ensure(ctx->d_gather, ctx->gather_cap, band_doubles))) return rc;
+    }
+    if ((rc = upload_points(ctx, x, y, z, kr, kc, n))) return rc;
+    if (s.rounds > 0 && nrows > 0 && grid->cols > 0)
+        if ((rc = launch_round(ctx, 0))) return rc;
+    s.active = true;
+    return V2R_IDW_OK;
+}
+
+// Delivers the next (device, sub-band).  out_base + e*plane_stride + row_off*cols receives exponent e.
+static int next_band(v2r_idw_ctx *ctx, double *out_base, long long plane_stride, bool pack, long long *o_row0, long long *o_nrows) {
+    Session &s = ctx->ses;
+    if (!s.active) return set_error(V2R_IDW_ESTATE, "no streaming session is open");
+    const int G = (int)ctx->dev.size();
+    const int E = (int)s.exps.size();
+    for (;;) {
+        if (s.cur_round >= s.rounds || s.grid.cols == 0) {
+            *o_row0 = s.row0 + s.nrows;
+            *o_nrows = 0;
+            return V2R_IDW_OK;
+        }
+        if (s.cur_dev == 0 && s.cur_round + 1 < s.rounds) {
+            int rc = launch_round(ctx, s.cur_round + 1);  // next round computes while this one is copied out
+            if (rc) return rc;
+        }
+        DeviceState &d = ctx->dev[s.cur_dev];
+        const int buf = (int)(s.cur_round & 1);
+        long long r0, nr;
+        sub_band(s, d, s.cur_round, &r0, &nr);
+        const int g = s.cur_dev;
+        if (++s.cur_dev == G) { s.cur_dev = 0; ++s.cur_round; }
+        if (nr <= 0) continue;
+
+        DeviceState &d0 = ctx->dev[0];
+        const double *src = d.d_band[buf];
+        const size_t cnt = (size_t)nr * (size_t)s.grid.cols * (size_t)E;
+        CUDA_TRY(cudaSetDevice(d.device));
+        CUDA_TRY(cudaStreamWaitEvent(d.copy, d.k_stop[buf], 0));
+        if (g != 0) {  // gather the band to rank 0 over NVLink (north_star), then copy out from there
+            NCCL_TRY(g_nccl.GroupStart());
+            NCCL_TRY(g_nccl.Send(src, cnt, ncclDouble, 0, d.comm, d.copy));
+            NCCL_TRY(g_nccl.Recv(ctx->d_gather, cnt, ncclDouble, g, d0.comm, d0.copy));
+            NCCL_TRY(g_nccl.GroupEnd());
+            src = ctx->d_gather;
+            CUDA_TRY(cudaSetDevice(d0.device));
+        }
+        CUDA_TRY(cudaEventRecord(d0.c_start, d0.copy));
+        const long long plane_src = nr * s.grid.cols;
+        const long long stride = pack ? plane_src : plane_stride;
+        const long long off = pack ? 0 : (r0 - s.row0) * s.grid.cols;
+        for (int e = 0; e < E; ++e)
+            CUDA_TRY(cudaMemcpyAsync(out_base + (long long)e * stride + off, src + (long long)e * plane_src,
+                                     (size_t)plane_src * 8, cudaMemcpyDeviceToHost, d0.copy));
+        CUDA_TRY(cudaEventRecord(d0.c_stop, d0.copy));
+        CUDA_TRY(cudaStreamSynchronize(d0.copy));
+        if (g != 0) {
+            CUDA_TRY(cudaSetDevice(d.device));
+            CUDA_TRY(cudaStreamSynchronize(d.copy));
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, d0.c_start, d0.c_stop);
+        ctx->d2h_ms += ms;
+        cudaEventElapsedTime(&ms, d.k_start[buf], d.k_stop[buf]);
+        d.kernel_ms += ms;
+        *o_row0 = r0;
+        *o_nrows = nr;
+        return V2R_IDW_OK;
+    }
+}
+
+static int end_session(v2r_idw_ctx *ctx) {
+    Session &s = ctx->ses;
+    if (!s.active) return set_error(V2R_IDW_ESTATE, "no streaming session is open");
+    int rc = V2R_IDW_OK;
+    for (auto &d : ctx->dev) {
+        cudaSetDevice(d.device);
+        cudaError_t ce = cudaStreamSynchronize(d.compute);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(d.copy);
+        if (ce != cudaSuccess && rc == V2R_IDW_OK) rc = set_error(V2R_IDW_ECUDA, "stream sync: %s", cudaGetErrorString(ce));
+        ctx->kernel_ms = std::max(ctx->kernel_ms, d.kernel_ms);
+    }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->dev[0].up_start, ctx->dev[0].up_stop) == cudaSuccess) ctx->h2d_ms = ms;
+    cudaGetLastError();
+    s.active = false;
+    return rc;
+}
+
+}  // namespace v2r
+
+using namespace v2r;
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+int v2r_idw_abi_version(void) { return V2R_IDW_ABI_VERSION; }
+const char *v2r_idw_last_error(void) { return last_error(); }
+
+int v2r_idw_device_count(int *count) {
+    if (!count) return set_error(V2R_IDW_EINVAL, "count is NULL");
+    cudaError_t ce = cudaGetDeviceCount(count);
+    if (ce != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return set_error(V2R_IDW_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(ce));
+    }
+    return V2R_IDW_OK;
+}
+
+int v2r_idw_init(int n_gpus, v2r_idw_ctx **out) {
+    if (!out) return set_error(V2R_IDW_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n_gpus != 1 && n_gpus != 2 && n_gpus != 4 && n_gpus != 8) return set_error(V2R_IDW_EINVAL, "n_gpus must be 1, 2, 4 or 8 (got %d)", n_gpus);
+    std::vector<int> devs(n_gpus);
+    for (int i = 0; i < n_gpus; ++i) devs[i] = i;
+    return create_ctx(devs, out);
+}
+
+int v2r_idw_init_device(int device, v2r_idw_ctx **out) {
+    if (!out) return set_error(V2R_IDW_EINVAL, "out is NULL");
+    *out = nullptr;
+    return create_ctx({device}, out);
+}
+
+void v2r_idw_destroy(v2r_idw_ctx *ctx) {
+    if (!ctx) return;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->d_gather) {
+            cudaSetDevice(ctx->dev[0].device);
+            cudaFree(ctx->d_gather);
+        }
+        for (auto &d : ctx->dev) free_device_state(d);
+    }
+    delete ctx;
+}
+
+int v2r_idw_alloc_pinned(size_t bytes, void **ptr) {
+    if (!ptr) return set_error(V2R_IDW_EINVAL, "ptr is NULL");
+    *ptr = nullptr;
+    cudaError_t ce = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(ce == cudaErrorMemoryAllocation ? V2R_IDW_ENOMEM : V2R_IDW_ECUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(ce));
+    }
+    return V2R_IDW_OK;
+}
+
+int v2r_idw_free_pinned(void *ptr) {
+    if (!ptr) return V2R_IDW_OK;
+    cudaError_t ce = cudaFreeHost(ptr);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(V2R_IDW_ECUDA, "cudaFreeHost: %s", cudaGetErrorString(ce));
+    }
+    return V2R_IDW_OK;
+}
+
+// ---- host helpers ---------------------------------------------------------------------------
+// Go's float64 -> int conversion on amd64: truncation; NaN / out of range -> INT64_MIN.
+static int64_t go_int(double v) {
+    if (!(v > -9223372036854775808.0 && v < 9223372036854775808.0)) return INT64_MIN;
+    return (int64_t)v;
+}
+
+int v2r_idw_get_dimensions(double x_min, double x_max, double x_step, double y_min, double y_max, double y_step,
+                           int64_t *rows, int64_t *cols) {
+    if (!rows || !cols) return set_error(V2R_IDW_EINVAL, "rows/cols is NULL");
+    *cols = go_int((1 + x_max - x_min) / x_step);
+    *rows = go_int((1 + y_max - y_min) / y_step);
+    return V2R_IDW_OK;
+}
+
+int v2r_idw_point_to_pair(double x, double y, double x_min, double x_step, double y_min, double y_step, int64_t *r,
+                          int64_t *c) {
+    if (!r || !c) return set_error(V2R_IDW_EINVAL, "r/c is NULL");
+    *r = go_int((y - y_min) / y_step);
+    *c = go_int((x - x_min) / x_step);
+    return V2R_IDW_OK;
+}
+
+int v2r_idw_exp_range(double es, double ee, double ei, double *out, int64_t max_out, int64_t *count) {
+    if (!count) return set_error(V2R_IDW_EINVAL, "count is NULL");
+    *count = 0;
+    if (!(ei > 0)) return set_error(V2R_IDW_EINVAL, "exponential increment (%g) must be > 0", ei);
+    if (!(ee > es)) return set_error(V2R_IDW_EINVAL, "exponent range: [%g, %g) has no iterations", es, ee);
+    int64_t n = 0;
+    for (double e = es; e < ee; e += ei) {
+        if (out && n < max_out) out[n] = e;
+        if (++n > (1 << 20)) return set_error(V2R_IDW_EINVAL, "exponent range has more than 2^20 steps");
+    }
+    *count = n;
+    return V2R_IDW_OK;
+}
+
+struct PairKey {
+    int64_t r, c;
+    bool operator==(const PairKey &o) const { return r == o.r && c == o.c; }
+};
+struct PairHash {
+    size_t operator()(const PairKey &k) const {
+        uint64_t h = (uint64_t)k.r * 0x9E3779B97F4A7C15ull + (uint64_t)k.c;
+        h ^= h >> 31;
+        h *= 0xD6E8FEB86659FD93ull;
+        h ^= h >> 32;
+        return (size_t)h;
+    }
+};
+
+int v2r_idw_make_coord_space(int64_t n, const double *x, const double *y, const double *z, double x_min,
+                             double x_step, double y_min, double y_step, double *ox, double *oy, double *oz,
+                             int64_t *okr, int64_t *okc, int64_t *n_out) {
+    if (!n_out) return set_error(V2R_IDW_EINVAL, "n_out is NULL");
+    *n_out = 0;
+    if (n < 0) return set_error(V2R_IDW_EINVAL, "n < 0");
+    if (n > 0 && (!x || !y || !z || !ox || !oy || !oz || !okr || !okc)) return set_error(V2R_IDW_EINVAL, "NULL array");
+    try {
+        std::unordered_map<PairKey, int64_t, PairHash> seen;
+        seen.reserve((size_t)n * 2);
+        int64_t cnt = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            PairKey k{go_int((y[i] - y_min) / y_step), go_int((x[i] - x_min) / x_step)};
+            auto it = seen.find(k);
+            double w = z[i];
+            int64_t slot;
+            if (it != seen.end()) {
+                slot = it->second;
+                w = (w + oz[slot]) / 2;  // tools/utils.go:111: newElev := (p.Weight + elev.Weight) / 2
+            } else {
+                slot = cnt++;
+                seen.emplace(k, slot);
+                okr[slot] = k.r;
+                okc[slot] = k.c;
+            }
+            ox[slot] = x[i];  // position of the last arrival is kept (tools/utils.go:115)
+            oy[slot] = y[i];
+            oz[slot] = w;
+        }
+        *n_out = cnt;
+    } catch (const std::bad_alloc &) {
+        return set_error(V2R_IDW_ENOMEM, "out of host memory in make_coord_space");
+    }
+    return V2R_IDW_OK;
+}
+
+// ---- solves -----------------------------------------------------------------------------------
+int v2r_idw_solve_rows(v2r_idw_ctx *ctx, const double *x, const double *y, const double *z, const int64_t *key_r,
+                       const int64_t *key_c, int64_t n, const v2r_idw_grid *grid, int64_t row0, int64_t nrows,
+                       const double *exps, int n_exps, int precision, double *out) {
+    if (!ctx) return set_error(V2R_IDW_EINVAL, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (grid && nrows > 0 && grid->cols > 0 && !out) return set_error(V2R_IDW_EINVAL, "out is NULL");
+    int rc = begin_session(ctx, x, y, z, key_r, key_c, n, grid, row0, nrows, exps, n_exps, precision, 0);
+    if (rc) return rc;
+    const long long plane = (long long)nrows * grid->cols;
+    for (;;) {
+        long long r0 = 0, nr = 0;
+        rc = next_band(ctx, out, plane, false, &r0, &nr);
+        if (rc || nr == 0) break;
+    }
+    int rc2 = end_session(ctx);
+    return rc ? rc : rc2;
+}
+
+int v2r_idw_solve(v2r_idw_ctx *ctx, const double *x, const double *y, const double *z, const int64_t *key_r,
+                  const int64_t *key_c, int64_t n, const v2r_idw_grid *grid, const double *exps, int n_exps,
+                  int precision, double *out) {
+    if (!grid) return set_error(V2R_IDW_EINVAL, "grid is NULL");
+    return v2r_idw_solve_rows(ctx, x, y, z, key_r, key_c, n, grid, 0, grid->rows, exps, n_exps, precision, out);
+}
+
+int v2r_idw_stream_begin(v2r_idw_ctx *ctx, const double *x, const double *y, const double *z, const int64_t *key_r,
+                         const int64_t *key_c, int64_t n, const v2r_idw_grid *grid, const double *exps, int n_exps,
+                         int precision, int64_t band_rows) {
+    if (!ctx) return set_error(V2R_IDW_EINVAL, "ctx is NULL");
+    if (!grid) return set_error(V2R_IDW_EINVAL, "grid is NULL");
+    if (band_rows < 0) return set_error(V2R_IDW_EINVAL, "band_rows < 0");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return begin_session(ctx, x, y, z, key_r, key_c, n, grid, 0, grid->rows, exps, n_exps, precision, band_rows);
+}
+
+int v2r_idw_stream_next(v2r_idw_ctx *ctx, double *out, int64_t *row0, int64_t *nrows) {
+    if (!ctx || !row0 || !nrows) return set_error(V2R_IDW_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!out && ctx->ses.active && ctx->ses.cur_round < ctx->ses.rounds && ctx->ses.grid.cols > 0)
+        return set_error(V2R_IDW_EINVAL, "out is NULL");
+    long long r0 = 0, nr = 0;
+    int rc = next_band(ctx, out, 0, true, &r0, &nr);
+    *row0 = r0;
+    *nrows = nr;
+    return rc;
+}
+
+int v2r_idw_stream_end(v2r_idw_ctx *ctx) {
+    if (!ctx) return set_error(V2R_IDW_EINVAL, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return end_session(ctx);
+}
+
+int v2r_idw_last_timing(v2r_idw_ctx *ctx, double *h2d_ms, double *kernel_ms, double *d2h_ms) {
+    if (!ctx) return set_error(V2R_IDW_EINVAL, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (h2d_ms) *h2d_ms = ctx->h2d_ms;
+    if (kernel_ms) *kernel_ms = ctx->kernel_ms;
+    if (d2h_ms) *d2h_ms = ctx->d2h_ms;
+    return V2R_IDW_OK;
+}
+
+}  // extern "C"

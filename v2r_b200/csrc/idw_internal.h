@@ -1,0 +1,37 @@
+// idw_internal.h -- declarations shared by the translation units of libv2r_idw.so.
+#pragma once
+#include <atomic>
+#include <cstdarg>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/v2r_idw.h"
+
+namespace v2r {
+
+// One kernel pass over the points: `count` consecutive exponents of the sweep starting at `first`.
+struct Pass {
+    int mode;         // Mode
+    int first, count; // exponent slice
+    int k0, dk;       // ladder classes: h_e = base^(k0 + e*dk)
+    double cexp[16];  // general class: c_e = -p_e / 2
+};
+
+int set_error(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+const char *last_error();
+
+int plan_sweep(const double *exps, int n_exps, std::vector<Pass> &passes);
+int validate_launch(const void *d_x, const void *d_y, const void *d_z, long long n, const v2r_idw_grid *g,
+                    long long row0, long long nrows, int n_exps, const void *d_out);
+int launch_rows_fp64(cudaStream_t stream, const double *d_x, const double *d_y, const double *d_z,
+                     const long long *d_kr, const long long *d_kc, long long n, const v2r_idw_grid &g,
+                     long long row0, long long nrows, const double *exps, int n_exps, double *d_out);
+int launch_rows_fp32(cudaStream_t stream, const double *d_x, const double *d_y, const double *d_z,
+                     const long long *d_kr, const long long *d_kc, long long n, const v2r_idw_grid &g,
+                     long long row0, long long nrows, const double *exps, int n_exps, double *d_out);
+std::string describe_fp32(const std::vector<Pass> &passes);
+long long launch_count();
+
+}  // namespace v2r

@@ -1,0 +1,312 @@
+// idw_kernels.cuh -- sm_100a kernels of the IDW gridding hot path (FP64 classes).
+//
+// Replaces the per-cell loop of the reference (features/idw/idw_utils.go:8-27 calculateIDW called
+// from features/idw/idw.go:34-40 and features/idw/idw_chunk.go:27-41):
+//     z(r,c) = sum_i w_i * d_i^-p / sum_i d_i^-p ,  d_i = |cell(r,c) - point_i|
+// for every cell of a row band, for E exponents in ONE pass over the points.
+//
+// Shape of the computation:
+//   * a CTA owns a tile of (WARPS*CR) rows x (32*CC) columns; a thread owns a CR x CC register block
+//     (lanes run along columns so the raster stores coalesce);
+//   * the point stream (SoA x[], y[], w[]) is brought into shared memory by 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx), STAGES deep; every thread reads the same point at the
+//     same time, i.e. shared-memory broadcasts;
+//   * per point and thread: CR squared dy and CC squared dx (reference: Pow(dx,2), Pow(dy,2),
+//     tools/utils.go:157 -- both exactly rounded products), then per pair ONE add d2 = dx2 + dy2
+//     (bit-identical to the reference's `total`), the power d2^(-p/2), one FMA and one ADD;
+//   * d^-p never goes through sqrt+pow: it is rcp / rsqrt / fourth-root seeds from MUFU.RCP64H /
+//     MUFU.RSQ64H refined by one cubic step in the FP64 pipe, or exp2(c*log2 d2) for general p.
+//
+// No tensor cores: this is not a contraction (every pair needs its own reciprocal power).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace v2r {
+
+enum Mode : int {
+    MODE_RCP = 0,  // all p are positive even integers : base b = 1/d2,        h = b^(p/2)
+    MODE_RSQ = 1,  // all p are positive integers      : base b = d2^(-1/2),   h = b^p
+    MODE_QRT = 2,  // all p are positive multiples of .5: base b = d2^(-1/4),  h = b^(2p)
+    MODE_GEN = 3   // anything else (incl. p <= 0)      : h = exp2(c * log2 d2), c = -p/2 ; p == 0 -> h = 1
+};
+
+constexpr int kMaxE = 10;        // exponents per pass (register budget); longer sweeps run several passes
+constexpr int kTilePoints = 512; // points per shared-memory stage
+constexpr int kStages = 3;
+
+struct KParams {
+    const double *x, *y, *w;  // device SoA, 16-byte aligned
+    long long n;              // number of points
+    double x_min, x_step, y_min, y_step;
+    long long cols;           // grid columns
+    long long row0, nrows;    // band [row0, row0 + nrows)
+    double *out;              // E planes of nrows*cols
+    long long plane;          // nrows * cols
+    int k0, dk;               // integer power ladder: h_e = b^(k0 + e*dk) (runtime variant)
+    double cexp[kMaxE];       // MODE_GEN: c_e = -p_e/2 (0 => h = 1)
+};
+
+// ---------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// MUFU.RCP64H / MUFU.RSQ64H: ~2^-20 relative seeds computed from the high word of the operand.
+__device__ __forceinline__ double rcp_seed(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    return r;
+}
+__device__ __forceinline__ double rsq_seed(double a) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    return r;
+}
+
+// ---------------------------------------------------------------------------- base powers
+// 1/a: seed + one cubic step (e = 1 - a r0 ; r = r0 (1 + e + e^2)); truncation e^3 ~ 2^-60.
+// 3 FP64-pipe instructions + 1 MUFU.  a = 0 -> NaN (reference: +Inf weight -> Inf/Inf = NaN cell).
+__device__ __forceinline__ double pow_m1(double a) {
+    double r0 = rcp_seed(a);
+    double e = fma(-a, r0, 1.0);
+    double t = fma(e, e, e);
+    return fma(r0, t, r0);
+}
+// a^(-1/2): e = 1 - a y0^2 ; y = y0 (1 + e/2 + 3 e^2/8).  5 FP64 + 1 MUFU.
+__device__ __forceinline__ double pow_m12(double a) {
+    double y0 = rsq_seed(a);
+    double t = a * y0;
+    double e = fma(-t, y0, 1.0);
+    double p = fma(e, 0.375, 0.5);
+    double ye = y0 * e;
+    return fma(ye, p, y0);
+}
+// a^(-1/4): q0 = rsq(a) * rsq(rsq(a)); e = 1 - a q0^4 ; q = q0 (1 + e/4 + 5 e^2/32).  7 FP64 + 2 MUFU.
+__device__ __forceinline__ double pow_m14(double a) {
+    double y0 = rsq_seed(a);   // a^-1/2 (low word 0, so the second seed sees it exactly)
+    double z0 = rsq_seed(y0);  // a^+1/4
+    double q0 = y0 * z0;       // a^-1/4, ~2^-20
+    double q2 = q0 * q0;
+    double t = a * q2;
+    double e = fma(-t, q2, 1.0);
+    double p = fma(e, 0.15625, 0.25);
+    double qe = q0 * e;
+    return fma(qe, p, q0);
+}
+
+template <int K>
+__device__ __forceinline__ double ipow_c(double b) {
+    static_assert(K >= 1, "power must be positive");
+    if constexpr (K == 1) {
+        return b;
+    } else if constexpr (K % 2 == 0) {
+        double h = ipow_c<K / 2>(b);
+        return h * h;
+    } else {
+        return ipow_c<K - 1>(b) * b;
+    }
+}
+// runtime (warp-uniform) power, k >= 1
+__device__ __forceinline__ double ipow_rt(double b, int k) {
+    double r = b;
+    bool have = (k & 1);
+    k >>= 1;
+    while (k) {
+        b *= b;
+        if (k & 1) { r = have ? r * b : b; have = true; }
+        k >>= 1;
+    }
+    return r;
+}
+
+template <int MODE>
+__device__ __forceinline__ double base_pow(double d2) {
+    if constexpr (MODE == MODE_RCP) return pow_m1(d2);
+    else if constexpr (MODE == MODE_RSQ) return pow_m12(d2);
+    else return pow_m14(d2);
+}
+
+// h[e] = d2^(-p_e/2) for all exponents of the pass.
+template <int MODE, int E, int K0, int DK>
+__device__ __forceinline__ void weights(double d2, const KParams &p, double (&h)[E]) {
+    if constexpr (MODE == MODE_GEN) {
+        double L = log2(d2);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            double c = p.cexp[e];
+            h[e] = (c == 0.0) ? 1.0 : exp2(c * L);  // Go: Pow(d, -0) == 1 even at d == 0
+        }
+    } else {
+        double b = base_pow<MODE>(d2);
+        if constexpr (K0 > 0) {
+            h[0] = ipow_c<K0>(b);
+        } else {
+            h[0] = ipow_rt(b, p.k0);
+        }
+        if constexpr (E > 1) {
+            double m;
+            if constexpr (K0 > 0) {
+                m = ipow_c<(DK > 0 ? DK : 1)>(b);
+            } else {
+                m = ipow_rt(b, p.dk);
+            }
+#pragma unroll
+            for (int e = 1; e < E; ++e) h[e] = h[e - 1] * m;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- main kernel
+template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) idw_fp64_kernel(const __grid_constant__ KParams p) {
+    constexpr int WARPS = THREADS / 32;
+    constexpr int T = kTilePoints;
+    constexpr int S = kStages;
+    __shared__ __align__(128) double sm[S][3][T];
+    __shared__ __align__(8) uint64_t full[S];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long c_base = (long long)blockIdx.x * (32 * CC) + lane;
+    const long long r_base = p.row0 + ((long long)blockIdx.y * WARPS + warp) * CR;
+
+    // RCToPoint (tools/utils.go:78-82): px = xMin + float64(c)*xStep, multiply then add, unfused.
+    double cx[CC], cy[CR];
+#pragma unroll
+    for (int b = 0; b < CC; ++b) cx[b] = __dadd_rn(p.x_min, __dmul_rn((double)(c_base + 32 * b), p.x_step));
+#pragma unroll
+    for (int a = 0; a < CR; ++a) cy[a] = __dadd_rn(p.y_min, __dmul_rn((double)(r_base + a), p.y_step));
+
+    double num[E][CR][CC], den[E][CR][CC];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+#pragma unroll
+        for (int a = 0; a < CR; ++a)
+#pragma unroll
+            for (int b = 0; b < CC; ++b) { num[e][a][b] = 0.0; den[e][a][b] = 0.0; }
+
+    const long long ntiles = (p.n + T - 1) / T;
+    const long long nfull = p.n / T;  // tiles fetched by TMA; a ragged last tile is loaded by the threads
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](long long t) {
+        const int s = (int)(t % S);
+        mbar_expect_tx(&full[s], 3u * T * (uint32_t)sizeof(double));
+        tma_load_1d(&sm[s][0][0], p.x + t * T, T * (uint32_t)sizeof(double), &full[s]);
+        tma_load_1d(&sm[s][1][0], p.y + t * T, T * (uint32_t)sizeof(double), &full[s]);
+        tma_load_1d(&sm[s][2][0], p.w + t * T, T * (uint32_t)sizeof(double), &full[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (long long t = 0; t < S - 1 && t < nfull; ++t) issue(t);
+    }
+
+    for (long long t = 0; t < ntiles; ++t) {
+        const int s = (int)(t % S);
+        int cnt = T;
+        // stage (t-1)%S was released by the __syncthreads that ended iteration t-1
+        if (threadIdx.x == 0 && t + S - 1 < nfull) issue(t + S - 1);
+        if (t < nfull) {
+            mbar_wait(&full[s], (uint32_t)((t / S) & 1));
+        } else {
+            cnt = (int)(p.n - t * T);
+            for (int i = threadIdx.x; i < cnt; i += THREADS) {
+                sm[s][0][i] = p.x[t * T + i];
+                sm[s][1][i] = p.y[t * T + i];
+                sm[s][2][i] = p.w[t * T + i];
+            }
+            __syncthreads();
+        }
+        const double *sx = sm[s][0], *sy = sm[s][1], *sw = sm[s][2];
+#pragma unroll 1
+        for (int i = 0; i < cnt; ++i) {
+            const double x = sx[i], y = sy[i], w = sw[i];
+            double dx2[CC], dy2[CR];
+            // euclidDist(p, p0): point minus cell, each square rounded on its own (tools/utils.go:157)
+#pragma unroll
+            for (int b = 0; b < CC; ++b) { double d = __dsub_rn(x, cx[b]); dx2[b] = __dmul_rn(d, d); }
+#pragma unroll
+            for (int a = 0; a < CR; ++a) { double d = __dsub_rn(y, cy[a]); dy2[a] = __dmul_rn(d, d); }
+#pragma unroll
+            for (int a = 0; a < CR; ++a)
+#pragma unroll
+                for (int b = 0; b < CC; ++b) {
+                    const double d2 = __dadd_rn(dx2[b], dy2[a]);
+                    double h[E];
+                    weights<MODE, E, K0, DK>(d2, p, h);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        num[e][a][b] = fma(w, h[e], num[e][a][b]);
+                        den[e][a][b] += h[e];
+                    }
+                }
+        }
+        __syncthreads();
+    }
+
+    const long long row_end = p.row0 + p.nrows;
+#pragma unroll
+    for (int a = 0; a < CR; ++a) {
+        const long long r = r_base + a;
+        if (r >= row_end) continue;
+#pragma unroll
+        for (int b = 0; b < CC; ++b) {
+            const long long c = c_base + 32 * b;
+            if (c >= p.cols) continue;
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                p.out[(long long)e * p.plane + (r - p.row0) * p.cols + c] = num[e][a][b] / den[e][a][b];
+        }
+    }
+}
+
+// Exact-hit rule (features/idw/idw_utils.go:13-16): every keyed cell returns its point's weight,
+// for every exponent.  Runs after the main kernel on the same stream.
+__global__ void idw_patch_exact_kernel(const double *__restrict__ w, const long long *__restrict__ kr,
+                                       const long long *__restrict__ kc, long long n, long long cols,
+                                       long long row0, long long nrows, double *__restrict__ out,
+                                       long long plane, int n_exps) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long r = kr[i], c = kc[i];
+    if (r < row0 || r >= row0 + nrows || c < 0 || c >= cols) return;
+    double v = w[i];
+    for (int e = 0; e < n_exps; ++e) out[(long long)e * plane + (r - row0) * cols + c] = v;
+}
+
+}  // namespace v2r

@@ -1,0 +1,375 @@
+// idw_launch.cu -- exponent classification, kernel dispatch and the device-level C-ABI entry
+// (v2r_idw_launch_rows, v2r_idw_describe, v2r_idw_measure_peaks).  See include/v2r_idw.h.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "idw_internal.h"
+#include "idw_kernels.cuh"
+#include "idw_kernels_fp32.cuh"
+
+namespace v2r {
+
+// ------------------------------------------------------------------------------------------
+// Sweep classification.  The host accumulates exponents in FP64
+// (cmd/idw.go:153), so class membership is decided on the exact double that arrives.
+// ------------------------------------------------------------------------------------------
+static bool is_int(double v) { return std::floor(v) == v; }
+
+int plan_sweep(const double *exps, int n_exps, std::vector<Pass> &passes) {
+    passes.clear();
+    if (!exps || n_exps < 1 || n_exps > 64) return set_error(V2R_IDW_EINVAL, "n_exps must be in [1, 64]");
+    for (int e = 0; e < n_exps; ++e)
+        if (!std::isfinite(exps[e])) return set_error(V2R_IDW_EINVAL, "exponent %d is not finite", e);
+
+    bool half = true, whole = true, even = true;
+    for (int e = 0; e < n_exps; ++e) {
+        const double p = exps[e];
+        if (!(p > 0.0) || !is_int(2.0 * p) || p > 32.0) half = false;
+        if (!is_int(p)) whole = false;
+        if (!is_int(p / 2.0)) even = false;
+    }
+    if (!half) {
+        for (int e0 = 0; e0 < n_exps;) {
+            const int left = n_exps - e0;
+            const int chunks = (left + kMaxE - 1) / kMaxE;
+            const int len = (left + chunks - 1) / chunks;
+            Pass ps{};
+            ps.mode = MODE_GEN;
+            ps.first = e0;
+            ps.count = len;
+            for (int i = 0; i < len; ++i) ps.cexp[i] = -exps[e0 + i] / 2.0;
+            passes.push_back(ps);
+            e0 += len;
+        }
+        return V2R_IDW_OK;
+    }
+    const int mode = even ? MODE_RCP : (whole ? MODE_RSQ : MODE_QRT);
+    const double unit = even ? 2.0 : (whole ? 1.0 : 0.5);
+    std::vector<int> k(n_exps);
+    for (int e = 0; e < n_exps; ++e) k[e] = (int)std::llround(exps[e] / unit);
+    bool ap = true;
+    const int dk = n_exps > 1 ? k[1] - k[0] : 0;
+    if (n_exps > 1 && dk < 1) ap = false;
+    for (int e = 2; e < n_exps && ap; ++e)
+        if (k[e] - k[e - 1] != dk) ap = false;
+    if (ap) {
+        for (int e0 = 0; e0 < n_exps;) {
+            const int left = n_exps - e0;
+            const int chunks = (left + kMaxE - 1) / kMaxE;
+            const int len = (left + chunks - 1) / chunks;
+            Pass ps{};
+            ps.mode = mode;
+            ps.first = e0;
+            ps.count = len;
+            ps.k0 = k[e0];
+            ps.dk = len > 1 ? dk : 0;
+            passes.push_back(ps);
+            e0 += len;
+        }
+    } else {  // arbitrary list: one pass per exponent, each in its own best class
+        for (int e = 0; e < n_exps; ++e) {
+            std::vector<Pass> one;
+            int rc = plan_sweep(exps + e, 1, one);
+            if (rc) return rc;
+            one[0].first = e;
+            passes.push_back(one[0]);
+        }
+    }
+    return V2R_IDW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel table
+// ------------------------------------------------------------------------------------------
+struct Variant {
+    int mode, E, k0, dk;  // k0 == 0: runtime ladder
+    int cr, cc, threads;
+    void (*fn)(const KParams);
+    const char *name;
+};
+
+#define V2R_VARIANT(MODE, E, CR, CC, K0, DK, THREADS, MINB) \
+    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE }
+
+// Cell block per thread shrinks as E grows (2*E*CR*CC FP64 accumulators live in registers).
+#define V2R_ROW(MODE)                                                                                  \
+    V2R_VARIANT(MODE, 1, 4, 4, 0, 0, 256, 1), V2R_VARIANT(MODE, 2, 2, 4, 0, 0, 256, 1),                \
+        V2R_VARIANT(MODE, 3, 2, 2, 0, 0, 256, 2), V2R_VARIANT(MODE, 4, 2, 2, 0, 0, 256, 2),            \
+        V2R_VARIANT(MODE, 5, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE, 6, 2, 2, 0, 0, 256, 1),            \
+        V2R_VARIANT(MODE, 7, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE, 8, 2, 2, 0, 0, 256, 1),            \
+        V2R_VARIANT(MODE, 9, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE, 10, 2, 2, 0, 0, 256, 1)
+
+static const Variant kVariants[] = {
+    // compile-time ladders for the headline shapes (looked up first)
+    V2R_VARIANT(MODE_RCP, 1, 4, 4, 1, 0, 256, 1),   // p = 2                    (configs c2, c4)
+    V2R_VARIANT(MODE_RSQ, 1, 4, 4, 1, 0, 256, 1),   // p = 1
+    V2R_VARIANT(MODE_RSQ, 1, 4, 4, 3, 0, 256, 1),   // p = 3
+    V2R_VARIANT(MODE_QRT, 1, 4, 4, 1, 0, 256, 1),   // p = 0.5
+    V2R_VARIANT(MODE_QRT, 1, 4, 4, 3, 0, 256, 1),   // p = 1.5 (the CLI default --es 1.5)
+    V2R_VARIANT(MODE_QRT, 9, 2, 2, 1, 1, 256, 1),   // p = 0.5 .. 4.5 step 0.5  (config c3)
+    V2R_VARIANT(MODE_QRT, 4, 2, 2, 2, 1, 256, 2),   // p = 1, 1.5, 2, 2.5       (config c5)
+    // runtime ladders
+    V2R_ROW(MODE_RCP), V2R_ROW(MODE_RSQ), V2R_ROW(MODE_QRT),
+    // general exponents: fewer cells per thread (log2/exp2 temporaries)
+    V2R_VARIANT(MODE_GEN, 1, 2, 2, 0, 0, 256, 2), V2R_VARIANT(MODE_GEN, 2, 2, 2, 0, 0, 256, 2),
+    V2R_VARIANT(MODE_GEN, 3, 2, 2, 0, 0, 256, 2), V2R_VARIANT(MODE_GEN, 4, 2, 2, 0, 0, 256, 2),
+    V2R_VARIANT(MODE_GEN, 5, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE_GEN, 6, 2, 2, 0, 0, 256, 1),
+    V2R_VARIANT(MODE_GEN, 7, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE_GEN, 8, 2, 2, 0, 0, 256, 1),
+    V2R_VARIANT(MODE_GEN, 9, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE_GEN, 10, 2, 2, 0, 0, 256, 1),
+};
+
+static const Variant *pick_variant(const Pass &ps) {
+    const Variant *fallback = nullptr;
+    for (const Variant &v : kVariants) {
+        if (v.mode != ps.mode || v.E != ps.count) continue;
+        if (ps.mode == MODE_GEN) return &v;
+        if (v.k0 == ps.k0 && v.dk == ps.dk) return &v;
+        if (v.k0 == 0 && !fallback) fallback = &v;
+    }
+    return fallback;
+}
+
+static const char *mode_name(int m) {
+    switch (m) {
+        case MODE_RCP: return "rcp";
+        case MODE_RSQ: return "rsqrt";
+        case MODE_QRT: return "root4";
+        default: return "general";
+    }
+}
+
+// FP64-pipe instruction model per cell-point pair.
+static double model_ops(const Pass &ps, const Variant &v) {
+    const int E = ps.count;
+    double per_point = 2.0 * (v.cr + v.cc) / double(v.cr * v.cc);  // dx, dx^2, dy, dy^2 amortised
+    double ops = per_point + 1.0 /* d2 */ + 2.0 * E /* fma + add */;
+    auto ladder = [](int k) {  // multiplies of square-and-multiply
+        int m = 0, hi = 0;
+        for (int b = 0; b < 31; ++b)
+            if (k >> b & 1) { hi = b; ++m; }
+        return hi + m - 1;
+    };
+    if (ps.mode == MODE_GEN) {
+        ops += 30.0 + 25.0 * E;  // software log2 once, exp2 per exponent (approximate)
+    } else {
+        ops += ps.mode == MODE_RCP ? 3 : (ps.mode == MODE_RSQ ? 5 : 7);
+        ops += ladder(ps.k0);
+        if (E > 1) ops += ladder(ps.dk) + (E - 1);
+    }
+    return ops;
+}
+
+static std::atomic<long long> g_launches{0};
+long long launch_count() { return g_launches.load(); }
+
+int launch_rows_fp64(cudaStream_t stream, const double *d_x, const double *d_y, const double *d_z,
+                     const long long *d_kr, const long long *d_kc, long long n, const v2r_idw_grid &g,
+                     long long row0, long long nrows, const double *exps, int n_exps, double *d_out) {
+    std::vector<Pass> passes;
+    int rc = plan_sweep(exps, n_exps, passes);
+    if (rc) return rc;
+    const long long plane = nrows * g.cols;
+    for (const Pass &ps : passes) {
+        const Variant *v = pick_variant(ps);
+        if (!v) return set_error(V2R_IDW_EINVAL, "no kernel variant for mode %d E %d", ps.mode, ps.count);
+        KParams kp{};
+        kp.x = d_x; kp.y = d_y; kp.w = d_z; kp.n = n;
+        kp.x_min = g.x_min; kp.x_step = g.x_step; kp.y_min = g.y_min; kp.y_step = g.y_step;
+        kp.cols = g.cols; kp.row0 = row0; kp.nrows = nrows;
+        kp.out = d_out + (long long)ps.first * plane;
+        kp.plane = plane;
+        kp.k0 = ps.k0 > 0 ? ps.k0 : 1;
+        kp.dk = ps.dk > 0 ? ps.dk : 1;
+        for (int i = 0; i < ps.count; ++i) kp.cexp[i] = ps.cexp[i];
+        const long long tile_r = (long long)(v->threads / 32) * v->cr, tile_c = 32LL * v->cc;
+        const long long gx = (g.cols + tile_c - 1) / tile_c, gy = (nrows + tile_r - 1) / tile_r;
+        if (gx > 2147483647LL || gy > 65535LL)
+            return set_error(V2R_IDW_EINVAL, "band of %lld rows x %lld cols exceeds one launch; use smaller bands", nrows, g.cols);
+        v->fn<<<dim3((unsigned)gx, (unsigned)gy), v->threads, 0, stream>>>(kp);
+        g_launches++;
+        cudaError_t ce = cudaGetLastError();
+        if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "idw kernel launch: %s", cudaGetErrorString(ce));
+    }
+    if (n > 0 && d_kr && d_kc) {
+        const int tb = 256;
+        idw_patch_exact_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, stream>>>(d_z, d_kr, d_kc, n, g.cols, row0, nrows,
+                                                                               d_out, plane, n_exps);
+        g_launches++;
+        cudaError_t ce = cudaGetLastError();
+        if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "patch kernel launch: %s", cudaGetErrorString(ce));
+    }
+    return V2R_IDW_OK;
+}
+
+int validate_launch(const void *d_x, const void *d_y, const void *d_z, long long n, const v2r_idw_grid *g,
+                    long long row0, long long nrows, int n_exps, const void *d_out) {
+    if (!g) return set_error(V2R_IDW_EINVAL, "grid is NULL");
+    if (n < 0) return set_error(V2R_IDW_EINVAL, "n < 0");
+    if (n > 0 && (!d_x || !d_y || !d_z)) return set_error(V2R_IDW_EINVAL, "point arrays are NULL");
+    if (g->rows < 0 || g->cols < 0) return set_error(V2R_IDW_EINVAL, "negative grid dimensions");
+    if (row0 < 0 || nrows < 0 || row0 + nrows > g->rows)
+        return set_error(V2R_IDW_EINVAL, "rows [%lld, %lld) outside the grid of %lld rows", row0, row0 + nrows, (long long)g->rows);
+    if (n_exps < 1 || n_exps > 64) return set_error(V2R_IDW_EINVAL, "n_exps must be in [1, 64]");
+    if (nrows > 0 && g->cols > 0 && !d_out) return set_error(V2R_IDW_EINVAL, "out is NULL");
+    if (((uintptr_t)d_x | (uintptr_t)d_y | (uintptr_t)d_z) & 15)
+        return set_error(V2R_IDW_EINVAL, "device point arrays must be 16-byte aligned (TMA bulk copies)");
+    return V2R_IDW_OK;
+}
+
+}  // namespace v2r
+
+using namespace v2r;
+
+extern "C" int v2r_idw_launch_rows(int device, void *stream, const double *d_x, const double *d_y,
+                                   const double *d_z, const int64_t *d_key_r, const int64_t *d_key_c,
+                                   int64_t n, const v2r_idw_grid *grid, int64_t row0, int64_t nrows,
+                                   const double *exps, int n_exps, int precision, double *d_out) {
+    int rc = validate_launch(d_x, d_y, d_z, n, grid, row0, nrows, n_exps, d_out);
+    if (rc) return rc;
+    if (precision != V2R_IDW_FP64 && precision != V2R_IDW_FP32) return set_error(V2R_IDW_EINVAL, "unknown precision %d", precision);
+    if (nrows == 0 || grid->cols == 0) return V2R_IDW_OK;
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(ce));
+    if (precision == V2R_IDW_FP32)
+        return launch_rows_fp32((cudaStream_t)stream, d_x, d_y, d_z, (const long long *)d_key_r, (const long long *)d_key_c, n,
+                                *grid, row0, nrows, exps, n_exps, d_out);
+    return launch_rows_fp64((cudaStream_t)stream, d_x, d_y, d_z, (const long long *)d_key_r, (const long long *)d_key_c, n,
+                            *grid, row0, nrows, exps, n_exps, d_out);
+}
+
+extern "C" int v2r_idw_describe(const double *exps, int n_exps, int precision, char *buf, size_t buf_len,
+                                double *fp64_ops_per_pair) {
+    std::vector<Pass> passes;
+    int rc = plan_sweep(exps, n_exps, passes);
+    if (rc) return rc;
+    std::string s;
+    double ops = 0;
+    if (precision == V2R_IDW_FP32) {
+        s = describe_fp32(passes);
+    } else {
+        for (const Pass &ps : passes) {
+            const Variant *v = pick_variant(ps);
+            if (!v) return set_error(V2R_IDW_EINVAL, "no kernel variant");
+            char tmp[160];
+            snprintf(tmp, sizeof tmp, "%sfp64/%s E=%d cells=%dx%d k0=%d dk=%d%s", s.empty() ? "" : " + ", mode_name(ps.mode),
+                     ps.count, v->cr, v->cc, ps.k0, ps.dk, v->k0 ? " (static ladder)" : "");
+            s += tmp;
+            ops += model_ops(ps, *v);
+        }
+    }
+    if (buf && buf_len) {
+        strncpy(buf, s.c_str(), buf_len - 1);
+        buf[buf_len - 1] = 0;
+    }
+    if (fp64_ops_per_pair) *fp64_ops_per_pair = ops;
+    return V2R_IDW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Roofline denominators: issue-rate microbenchmarks (MEASURED_PEAKS.json has no FP64 entry).
+// ------------------------------------------------------------------------------------------
+namespace v2r {
+template <int WHICH>
+__global__ void __launch_bounds__(256) peak_kernel(double *out, int iters) {
+    const double s = 1.0 + 1e-9 * threadIdx.x;
+    if constexpr (WHICH == 0) {  // DFMA
+        double a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = s + j;
+        for (int i = 0; i < iters; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = fma(a[j], 0.999999, 1e-7);
+        double t = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += a[j];
+        if (t == 12345.678) out[0] = t;
+    } else if constexpr (WHICH == 1) {  // MUFU.RCP64H
+        double a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = s + j;
+        for (int i = 0; i < iters; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = rcp_seed(a[j]);
+        double t = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += a[j];
+        if (t == 12345.678) out[0] = t;
+    } else if constexpr (WHICH == 2) {  // MUFU.RCP (fp32)
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = (float)s + j;
+        for (int i = 0; i < iters; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
+        float t = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += a[j];
+        if (t == 12345.678f) out[0] = t;
+    } else {  // FFMA
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = (float)s + j;
+        const float m = 0.999999f + 1e-9f * threadIdx.x, c = 1e-7f * threadIdx.x;
+        for (int i = 0; i < iters; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], m, c);
+        float t = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += a[j];
+        if (t == 12345.678f) out[0] = t;
+    }
+}
+
+template <int WHICH>
+static int run_peak(double ms_target, int sms, double *ginst) {
+    double *d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return set_error(V2R_IDW_ENOMEM, "cudaMalloc");
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    const int blocks = sms * 8;
+    int iters = 2000;
+    float ms = 0;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(a);
+        peak_kernel<WHICH><<<blocks, 256>>>(d, iters);
+        g_launches++;
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) {
+            cudaFree(d);
+            return set_error(V2R_IDW_ECUDA, "peak kernel: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        cudaEventElapsedTime(&ms, a, b);
+        double rate = (double)blocks * 256 * iters * 8 / (ms * 1e-3) / 1e9;
+        if (rep > 0 && rate > best) best = rate;
+        if (ms < ms_target) iters = (int)(iters * (ms_target / (ms > 0.01f ? ms : 0.01f)));
+        if (iters > 4000000) iters = 4000000;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *ginst = best;
+    return V2R_IDW_OK;
+}
+}  // namespace v2r
+
+extern "C" int v2r_idw_measure_peaks(int device, double ms, double *dfma, double *mufu64, double *mufu32, double *ffma) {
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(ce));
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (ms <= 0) ms = 50;
+    double v;
+    int rc;
+    if (dfma) { if ((rc = run_peak<0>(ms, sms, &v))) return rc; *dfma = v; }
+    if (mufu64) { if ((rc = run_peak<1>(ms, sms, &v))) return rc; *mufu64 = v; }
+    if (mufu32) { if ((rc = run_peak<2>(ms, sms, &v))) return rc; *mufu32 = v; }
+    if (ffma) { if ((rc = run_peak<3>(ms, sms, &v))) return rc; *ffma = v; }
+    return V2R_IDW_OK;
+}
+
+extern "C" int64_t v2r_idw_launch_count(void) { return launch_count(); }
