@@ -37,6 +37,15 @@ def o_ps(ps):
     return O.PointSet(ps.x, ps.y, ps.w, ps.key_r, ps.key_c)
 
 
+def oracle_ref(ps, xi, yi, p, rows=None, cols=None):
+    """(reference raster, tolerance scale sum|w|h/sum h) from the threaded oracle (bit-identical to its
+    serial FullSolve, tests/test_oracle_golden.py); the scale is the same IDW run on |w|."""
+    ref = O.chunk_solve(o_ps(ps), o_info(xi), o_info(yi), 8, 64, p, rows, cols)
+    absw = O.PointSet(ps.x, ps.y, np.abs(ps.w), ps.key_r, ps.key_c)
+    scale = O.chunk_solve(absw, o_info(xi), o_info(yi), 8, 64, p, rows, cols)
+    return ref, scale
+
+
 def assert_parity(z, z_ref, scale, rel=REL, what=""):
     z, z_ref, scale = np.asarray(z), np.asarray(z_ref), np.asarray(scale)
     assert z.shape == z_ref.shape
@@ -108,10 +117,9 @@ CLASSES = [2.0, 4.0, 1.0, 3.0, 5.0, 0.5, 1.5, 2.5, 1.7, 0.3, 0.30000000000000004
 
 @pytest.mark.parametrize("p", CLASSES)
 def test_random_1k_points_256_grid(ctx, p):
-    ps, xi, yi = random_case(11, 1000, 256, 256, step=3.0, x0=-50.0, y0=1e4)
+    ps, xi, yi = random_case(11, 1000, 256, 256, step=3.0, x0=-50.0, y0=1e4)  # 65 k cells x 1 k points
     z = V.solve(ps, xi, yi, [p], ctx=ctx)[0]
-    ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), p)
-    _, scale = O.full_solve_truth(o_ps(ps), o_info(xi), o_info(yi), p)
+    ref, scale = oracle_ref(ps, xi, yi, p)
     assert_parity(z, ref, scale, what=f"p={p}")
 
 
@@ -121,8 +129,7 @@ def test_tile_boundaries_and_ragged_grids(ctx, n):
     ps, xi, yi = random_case(100 + n, n, 37, 131, step=0.7)
     for p in (2.0, 1.5, 1.7):
         z = V.solve(ps, xi, yi, [p], ctx=ctx)[0]
-        ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), p)
-        _, scale = O.full_solve_truth(o_ps(ps), o_info(xi), o_info(yi), p)
+        ref, scale = oracle_ref(ps, xi, yi, p)
         assert_parity(z, ref, scale, what=f"n={n} p={p}")
 
 
@@ -134,8 +141,7 @@ def test_sweeps_match_single_exponent_solves(ctx):
         zs = V.solve(ps, xi, yi, exps, ctx=ctx)
         assert zs.shape == (len(exps), 96, 160)
         for e, p in enumerate(exps):
-            ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), float(p))
-            _, scale = O.full_solve_truth(o_ps(ps), o_info(xi), o_info(yi), float(p))
+            ref, scale = oracle_ref(ps, xi, yi, float(p))
             assert_parity(zs[e], ref, scale, what=f"sweep {exps} e={e}")
 
 
@@ -193,8 +199,7 @@ def test_epsg2284_magnitudes(ctx):
     ps, xi, yi = random_case(31, 800, 120, 120, step=100.0, x0=1.2020401943588393e+07, y0=3.885548111378168e+06, signed=False)
     for p in (2.0, 1.5):
         z = V.solve(ps, xi, yi, [p], ctx=ctx)[0]
-        ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), p)
-        _, scale = O.full_solve_truth(o_ps(ps), o_info(xi), o_info(yi), p)
+        ref, scale = oracle_ref(ps, xi, yi, p)
         assert_parity(z, ref, scale, what=f"epsg2284 p={p}")
 
 
@@ -204,8 +209,7 @@ def test_gpkg_fixture_end_to_end(golden_dir, ctx):
     ps = V.MakeCoordSpace(x, y, w, xi, yi)
     z = V.solve(ps, xi, yi, [1.5, 2.0], ctx=ctx)
     for e, p in enumerate((1.5, 2.0)):
-        ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), p)
-        _, scale = O.full_solve_truth(o_ps(ps), o_info(xi), o_info(yi), p)
+        ref, scale = oracle_ref(ps, xi, yi, p)
         assert_parity(z[e], ref, scale, what=f"gpkg p={p}")
 
 
@@ -281,3 +285,51 @@ def test_c3_sweep_full_width_band(ctx):
     for e, p in enumerate(exps):
         ref = O.solve_cells(o_ps(ps), o_info(xi), o_info(yi), float(p), rr, cc)
         assert_parity(z[e][rr - r0, cc], ref, np.abs(ref), what=f"c3 p={p}")   # w >= 0 so scale == |z|
+
+
+# --------------------------------------------------------------------------- FP32 fast path
+REL32 = 2e-5   # stated accuracy of the FP32 path: ~1e-5 relative (north_star); tests allow 2e-5
+
+
+@pytest.mark.parametrize("p", [2.0, 1.0, 3.0, 4.0, 0.5, 1.5, 1.7, 0.3])
+def test_fp32_path_random(ctx, p):
+    ps, xi, yi = random_case(41, 2000, 200, 300, step=25.0, signed=False)
+    z = V.solve(ps, xi, yi, [p], precision=_lib.FP32, ctx=ctx)[0]
+    ref, scale = oracle_ref(ps, xi, yi, p)
+    err = assert_parity(z, ref, scale, rel=REL32, what=f"fp32 p={p}")
+    assert err > 1e-12 or p == 0.0   # really the FP32 kernels, not the FP64 ones
+    assert np.array_equal(z[ps.key_r, ps.key_c], ps.w)   # exact hits stay bit-equal
+
+
+def test_fp32_path_epsg2284_magnitudes_and_signed_weights(ctx):
+    """1.2e7 ft coordinates: a plain float has a 1 ft ulp there; the CTA-local hi/lo split must hold 2e-5"""
+    ps, xi, yi = random_case(43, 3000, 160, 160, step=100.0, x0=1.2020401943588393e+07, y0=3.885548111378168e+06)
+    for exps in ([2.0], [1.0, 1.5, 2.0, 2.5]):
+        z = V.solve(ps, xi, yi, exps, precision=_lib.FP32, ctx=ctx)
+        for e, p in enumerate(exps):
+            ref, scale = oracle_ref(ps, xi, yi, p)
+            assert_parity(z[e], ref, scale, rel=REL32, what=f"fp32 epsg2284 p={p}")
+
+
+def test_fp32_tile_tails_and_nan(ctx):
+    for n in (0, 1, 2, 3, 511, 513, 1025):
+        ps, xi, yi = random_case(300 + n, n, 37, 131, step=0.7)
+        z = V.solve(ps, xi, yi, [2.0], precision=_lib.FP32, ctx=ctx)[0]
+        ref, scale = oracle_ref(ps, xi, yi, 2.0)
+        assert_parity(z, ref, scale, rel=REL32, what=f"fp32 n={n}")
+    xi, yi = V.Info(0, 3, 1), V.Info(0, 3, 1)
+    ps = V.PointSet(np.array([1.0, 3.0]), np.array([1.0, 2.0]), np.array([5.0, 9.0]),
+                    np.array([7, 2], np.int64), np.array([7, 3], np.int64))
+    z = V.solve(ps, xi, yi, [2.0], rows=4, cols=4, precision=_lib.FP32, ctx=ctx)[0]
+    assert np.isnan(z[1, 1]) and np.isnan(z).sum() == 1 and z[2, 3] == 9.0
+
+
+def test_fp32_c2_full_size_spot_check(ctx, c2):
+    ps, xi, yi, exps = c2
+    grid = make_grid(xi, yi)
+    z = ctx.solve(ps, grid, exps, _lib.FP32)[0]
+    rng = np.random.default_rng(6)
+    rr, cc = rng.integers(0, grid.rows, 300), rng.integers(0, grid.cols, 300)
+    ref = O.solve_cells(o_ps(ps), o_info(xi), o_info(yi), 2.0, rr, cc)
+    assert_parity(z[rr, cc], ref, np.abs(ref), rel=REL32, what="fp32 c2 spot check")
+    assert np.array_equal(z[ps.key_r, ps.key_c], ps.w)

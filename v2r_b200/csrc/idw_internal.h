@@ -33,5 +33,8 @@ int launch_rows_fp32(cudaStream_t stream, const double *d_x, const double *d_y, 
                      long long row0, long long nrows, const double *exps, int n_exps, double *d_out);
 std::string describe_fp32(const std::vector<Pass> &passes);
 long long launch_count();
+void count_launch();
+int launch_patch_exact(cudaStream_t stream, const double *d_z, const long long *d_kr, const long long *d_kc, long long n,
+                       const v2r_idw_grid &g, long long row0, long long nrows, double *d_out, int n_exps);
 
 }  // namespace v2r

@@ -295,18 +295,4 @@ __global__ void __launch_bounds__(THREADS, MINB) idw_fp64_kernel(const __grid_co
     }
 }
 
-// Exact-hit rule (features/idw/idw_utils.go:13-16): every keyed cell returns its point's weight,
-// for every exponent.  Runs after the main kernel on the same stream.
-__global__ void idw_patch_exact_kernel(const double *__restrict__ w, const long long *__restrict__ kr,
-                                       const long long *__restrict__ kc, long long n, long long cols,
-                                       long long row0, long long nrows, double *__restrict__ out,
-                                       long long plane, int n_exps) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    long long r = kr[i], c = kc[i];
-    if (r < row0 || r >= row0 + nrows || c < 0 || c >= cols) return;
-    double v = w[i];
-    for (int e = 0; e < n_exps; ++e) out[(long long)e * plane + (r - row0) * cols + c] = v;
-}
-
 }  // namespace v2r

@@ -8,7 +8,6 @@
 
 #include "idw_internal.h"
 #include "idw_kernels.cuh"
-#include "idw_kernels_fp32.cuh"
 
 namespace v2r {
 
@@ -164,6 +163,34 @@ static double model_ops(const Pass &ps, const Variant &v) {
 
 static std::atomic<long long> g_launches{0};
 long long launch_count() { return g_launches.load(); }
+void count_launch() { g_launches++; }
+
+// Exact-hit rule (features/idw/idw_utils.go:13-16): every keyed cell returns its point's weight,
+// for every exponent.  Runs after the main kernel on the same stream.
+__global__ void idw_patch_exact_kernel(const double *__restrict__ w, const long long *__restrict__ kr,
+                                       const long long *__restrict__ kc, long long n, long long cols,
+                                       long long row0, long long nrows, double *__restrict__ out,
+                                       long long plane, int n_exps) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long r = kr[i], c = kc[i];
+    if (r < row0 || r >= row0 + nrows || c < 0 || c >= cols) return;
+    double v = w[i];
+    for (int e = 0; e < n_exps; ++e) out[(long long)e * plane + (r - row0) * cols + c] = v;
+}
+
+int launch_patch_exact(cudaStream_t stream, const double *d_z, const long long *d_kr, const long long *d_kc, long long n,
+                       const v2r_idw_grid &g, long long row0, long long nrows, double *d_out, int n_exps) {
+    if (n <= 0 || !d_kr || !d_kc) return V2R_IDW_OK;
+    const int tb = 256;
+    idw_patch_exact_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, stream>>>(d_z, d_kr, d_kc, n, g.cols, row0, nrows, d_out,
+                                                                           nrows * g.cols, n_exps);
+    g_launches++;
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "patch kernel launch: %s", cudaGetErrorString(ce));
+    return V2R_IDW_OK;
+}
+
 
 int launch_rows_fp64(cudaStream_t stream, const double *d_x, const double *d_y, const double *d_z,
                      const long long *d_kr, const long long *d_kc, long long n, const v2r_idw_grid &g,
@@ -193,15 +220,7 @@ int launch_rows_fp64(cudaStream_t stream, const double *d_x, const double *d_y, 
         cudaError_t ce = cudaGetLastError();
         if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "idw kernel launch: %s", cudaGetErrorString(ce));
     }
-    if (n > 0 && d_kr && d_kc) {
-        const int tb = 256;
-        idw_patch_exact_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, stream>>>(d_z, d_kr, d_kc, n, g.cols, row0, nrows,
-                                                                               d_out, plane, n_exps);
-        g_launches++;
-        cudaError_t ce = cudaGetLastError();
-        if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "patch kernel launch: %s", cudaGetErrorString(ce));
-    }
-    return V2R_IDW_OK;
+    return launch_patch_exact(stream, d_z, d_kr, d_kc, n, g, row0, nrows, d_out, n_exps);
 }
 
 int validate_launch(const void *d_x, const void *d_y, const void *d_z, long long n, const v2r_idw_grid *g,
@@ -303,7 +322,7 @@ __global__ void __launch_bounds__(256) peak_kernel(double *out, int iters) {
         for (int j = 0; j < 8; ++j) a[j] = (float)s + j;
         for (int i = 0; i < iters; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
+            for (int j = 0; j < 8; ++j) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
         float t = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) t += a[j];
