@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--band-rows", type=int, default=0, help="rows of the rank's band per step (0 = the whole workload grid)")
+    ap.add_argument("--exps", default="", help="comma list overriding the workload's exponent sweep (diagnostics)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -185,6 +186,8 @@ def ours(args):
 
     # ---- workload: every rank keeps one workload-sized row band (weak scaling) ----------------
     x, y, w, xi, yi, exps = workloads.make(args.workload, scale_rows=world)
+    if args.exps:
+        exps = np.array([float(v) for v in args.exps.split(",")])
     ps = V.MakeCoordSpace(x, y, w, xi, yi)
     grid = make_grid(xi, yi)
     band = grid.rows // world
@@ -207,6 +210,7 @@ def ours(args):
     exps_c = np.ascontiguousarray(exps, dtype=np.float64)
 
     def step():
+        nonlocal nrows
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(L.v2r_idw_launch_rows(local, C.c_void_p(stream), C.c_void_p(dx.data_ptr()), C.c_void_p(dy.data_ptr()),
                                          C.c_void_p(dw.data_ptr()), C.c_void_p(dkr.data_ptr()), C.c_void_p(dkc.data_ptr()), n,
@@ -218,9 +222,15 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # warm-up: full steps for the default workload; for the minutes-long ones (c3-c5) 512-row bands are
+    # enough to bring clocks, caches and the instruction cache to steady state
+    full_nrows = nrows
+    if args.workload != "c2":
+        nrows = min(nrows, 512)
     for _ in range(max(args.warmup, 3)):
         step()
         flush.zero_()
+    nrows = full_nrows
     barrier()
     clocks = Clocks(local)
     if rank == 0:
@@ -263,25 +273,38 @@ def ours(args):
         _lib.check(L.v2r_idw_describe(C.c_void_p(exps_c.ctypes.data), E, prec, buf, 512, C.byref(ops)))
         A = ALGO_SLOTS[args.workload]
         per_gpu_pairs_s = value * 1e9 / world
-        achieved_tflops = per_gpu_pairs_s * 2 * A / 1e12
-        peak_tflops = 2 * dfma.value / 1e3
-        traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        traffic = None
         if os.path.exists(tpath):
             try:
                 traffic = json.load(open(tpath)).get(f"{args.workload}/{args.precision}")
             except Exception:
                 traffic = None
-        roofline = {
-            "bound": "fp64-pipe", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-            "frac": achieved_tflops / peak_tflops if peak_tflops else None, "traffic": traffic,
-            "peak_source": "in-run DFMA issue-rate microbenchmark (MEASURED_PEAKS.json has no FP64 entry)",
-            "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP64_TFLOPS,
-            "algorithmic_fp64_slots_per_pair": A, "issued_fp64_slots_per_pair_model": ops.value,
-            "fp64_pipe_busy_model": per_gpu_pairs_s * ops.value / (dfma.value * 1e9) if dfma.value else None,
-            "kernel": buf.value.decode(), "ms_per_launch": ms_total / args.steps,
-            "measured_peaks_ginst_s": {"dfma": dfma.value, "mufu_rcp64h": m64.value, "mufu_rcp_f32": m32.value, "ffma": ffma.value},
-        }
+        peaks = {"dfma": dfma.value, "mufu_rcp64h": m64.value, "mufu_rcp_f32": m32.value, "ffma": ffma.value}
+        if prec == _lib.FP64:
+            # FP64-pipe roofline: algorithmic slots per pair x 2 flop, against the DFMA issue rate
+            achieved_tflops = per_gpu_pairs_s * 2 * A / 1e12
+            peak_tflops = 2 * dfma.value / 1e3
+            roofline = {
+                "bound": "fp64-pipe", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+                "frac": achieved_tflops / peak_tflops if peak_tflops else None, "traffic": traffic,
+                "peak_source": "in-run DFMA issue-rate microbenchmark (MEASURED_PEAKS.json has no FP64 entry)",
+                "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP64_TFLOPS,
+                "algorithmic_fp64_slots_per_pair": A, "issued_fp64_slots_per_pair_model": ops.value,
+                "fp64_pipe_busy_model": per_gpu_pairs_s * ops.value / (dfma.value * 1e9) if dfma.value else None,
+                "kernel": buf.value.decode(), "ms_per_launch": ms_total / args.steps, "measured_peaks_ginst_s": peaks,
+            }
+        else:
+            # FP32 path: 4 FP32 slots + 1 MUFU.RCP per pair => MUFU-bound; flops counted as 2 x 4
+            achieved_tflops = per_gpu_pairs_s * 8 / 1e12
+            peak_tflops = m32.value * 8 / 1e3
+            roofline = {
+                "bound": "fp32 fma+mufu (MUFU-bound at 1 reciprocal per pair)", "achieved": achieved_tflops, "peak": peak_tflops,
+                "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops if peak_tflops else None, "traffic": traffic,
+                "peak_source": "in-run MUFU.RCP issue-rate microbenchmark; the paired-reciprocal kernel needs half a MUFU per pair, "
+                               "so its own bound is the FP32 FMA pipe", "peak_nominal": 4.65 * 8,
+                "kernel": buf.value.decode(), "ms_per_launch": ms_total / args.steps, "measured_peaks_ginst_s": peaks,
+            }
         cpu = None
         if not args.no_cpu_baseline:
             s = cpu_sample(args.workload, args.cpu_seconds)
@@ -294,7 +317,8 @@ def ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64" if prec == _lib.FP64 else "f32(tile)/f64(accumulate)",
             "data": "synthetic",
-            "config": {"workload": _workload_name(args.workload, world), "points_after_dedupe": n, "exponents": E,
+            "config": {"workload": _workload_name(args.workload, world) + (f" [exps overridden: {args.exps}]" if args.exps else ""),
+                       "points_after_dedupe": n, "exponents": E,
                        "rows_per_rank": nrows, "cols": int(grid.cols), "l2": "flushed between timed iterations (256 MiB memset); output band > L2",
                        "parallelism": f"row bands x{world}"},
             "pair_evals_per_step": pair_evals_step, "raster_evals_per_s_G": value * E,

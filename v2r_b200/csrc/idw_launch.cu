@@ -322,7 +322,11 @@ __global__ void __launch_bounds__(256) peak_kernel(double *out, int iters) {
         for (int j = 0; j < 8; ++j) a[j] = (float)s + j;
         for (int i = 0; i < iters; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
+            for (int j = 0; j < 8; ++j) {
+                float r;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a[j]));
+                a[j] = r + 0.5f;  // the FADD (FMA pipe) stops the compiler folding rcp(rcp(x)) -> x
+            }
         float t = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) t += a[j];
