@@ -2,6 +2,7 @@
 // (v2r_idw_launch_rows, v2r_idw_describe, v2r_idw_measure_peaks).  See include/v2r_idw.h.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -88,10 +89,11 @@ struct Variant {
     int cr, cc, threads;
     void (*fn)(const KParams);
     const char *name;
+    bool paired;
 };
 
 #define V2R_VARIANT(MODE, E, CR, CC, K0, DK, THREADS, MINB) \
-    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE }
+    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE, false }
 
 // Cell block per thread shrinks as E grows (2*E*CR*CC FP64 accumulators live in registers).
 #define V2R_ROW(MODE)                                                                                  \
@@ -103,7 +105,8 @@ struct Variant {
 
 static const Variant kVariants[] = {
     // compile-time ladders for the headline shapes (looked up first)
-    V2R_VARIANT(MODE_RCP, 1, 4, 4, 1, 0, 256, 1),   // p = 2                    (configs c2, c4)
+    Variant{MODE_RCP, 1, 1, 0, 4, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 4, 4, 1, 0, 256, 1, true>, "MODE_RCP", true},  // p = 2, paired (c2, c4)
+    V2R_VARIANT(MODE_RCP, 1, 4, 4, 1, 0, 256, 1),   // p = 2, one reciprocal per pair (V2R_IDW_FP64_PAIRED=0)
     V2R_VARIANT(MODE_RSQ, 1, 4, 4, 1, 0, 256, 1),   // p = 1
     V2R_VARIANT(MODE_RSQ, 1, 4, 4, 3, 0, 256, 1),   // p = 3
     V2R_VARIANT(MODE_QRT, 1, 4, 4, 1, 0, 256, 1),   // p = 0.5
@@ -121,8 +124,10 @@ static const Variant kVariants[] = {
 };
 
 static const Variant *pick_variant(const Pass &ps) {
+    static const bool allow_paired = !(getenv("V2R_IDW_FP64_PAIRED") && atoi(getenv("V2R_IDW_FP64_PAIRED")) == 0);
     const Variant *fallback = nullptr;
     for (const Variant &v : kVariants) {
+        if (v.paired && !allow_paired) continue;
         if (v.mode != ps.mode || v.E != ps.count) continue;
         if (ps.mode == MODE_GEN) return &v;
         if (v.k0 == ps.k0 && v.dk == ps.dk) return &v;
@@ -155,6 +160,7 @@ static double model_ops(const Pass &ps, const Variant &v) {
         ops += 30.0 + 25.0 * E;  // software log2 once, exp2 per exponent (approximate)
     } else {
         ops += ps.mode == MODE_RCP ? 3 : (ps.mode == MODE_RSQ ? 5 : 7);
+        if (v.paired) ops -= 0.5;  // 11 instead of 12 instructions per two pairs
         ops += ladder(ps.k0);
         if (E > 1) ops += ladder(ps.dk) + (E - 1);
     }
@@ -274,7 +280,7 @@ extern "C" int v2r_idw_describe(const double *exps, int n_exps, int precision, c
             if (!v) return set_error(V2R_IDW_EINVAL, "no kernel variant");
             char tmp[160];
             snprintf(tmp, sizeof tmp, "%sfp64/%s E=%d cells=%dx%d k0=%d dk=%d%s", s.empty() ? "" : " + ", mode_name(ps.mode),
-                     ps.count, v->cr, v->cc, ps.k0, ps.dk, v->k0 ? " (static ladder)" : "");
+                     ps.count, v->cr, v->cc, ps.k0, ps.dk, v->paired ? " (paired reciprocal)" : (v->k0 ? " (static ladder)" : ""));
             s += tmp;
             ops += model_ops(ps, *v);
         }
