@@ -90,10 +90,13 @@ struct Variant {
     void (*fn)(const KParams);
     const char *name;
     bool paired;
+    const char *tag;  // non-null: tuning build, selected only by V2R_IDW_TUNE=<tag>
 };
 
 #define V2R_VARIANT(MODE, E, CR, CC, K0, DK, THREADS, MINB) \
-    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE, false }
+    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE, false, nullptr }
+#define V2R_TUNE(TAG, MODE, E, CR, CC, K0, DK, THREADS, MINB) \
+    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE, false, TAG }
 
 // Cell block per thread shrinks as E grows (2*E*CR*CC FP64 accumulators live in registers).
 #define V2R_ROW(MODE)                                                                                  \
@@ -105,7 +108,11 @@ struct Variant {
 
 static const Variant kVariants[] = {
     // compile-time ladders for the headline shapes (looked up first)
-    Variant{MODE_RCP, 1, 1, 0, 4, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 4, 4, 1, 0, 256, 1, true>, "MODE_RCP", true},  // p = 2, paired (c2, c4)
+    // tuning builds (V2R_IDW_TUNE=<tag>), kept to document what was measured; never picked by default
+    V2R_TUNE("t384", MODE_RCP, 1, 4, 4, 1, 0, 384, 1), V2R_TUNE("t384", MODE_QRT, 1, 4, 4, 3, 0, 384, 1),
+    V2R_TUNE("b2", MODE_RCP, 1, 4, 2, 1, 0, 256, 2), V2R_TUNE("b2", MODE_QRT, 9, 1, 2, 1, 1, 256, 2),
+    V2R_TUNE("c1x4", MODE_QRT, 9, 1, 4, 1, 1, 256, 1), V2R_TUNE("b2", MODE_QRT, 1, 2, 4, 3, 0, 256, 2),
+    Variant{MODE_RCP, 1, 1, 0, 4, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 4, 4, 1, 0, 256, 1, true>, "MODE_RCP", true, nullptr},  // p = 2, paired (c2, c4)
     V2R_VARIANT(MODE_RCP, 1, 4, 4, 1, 0, 256, 1),   // p = 2, one reciprocal per pair (V2R_IDW_FP64_PAIRED=0)
     V2R_VARIANT(MODE_RSQ, 1, 4, 4, 1, 0, 256, 1),   // p = 1
     V2R_VARIANT(MODE_RSQ, 1, 4, 4, 3, 0, 256, 1),   // p = 3
@@ -125,8 +132,13 @@ static const Variant kVariants[] = {
 
 static const Variant *pick_variant(const Pass &ps) {
     static const bool allow_paired = !(getenv("V2R_IDW_FP64_PAIRED") && atoi(getenv("V2R_IDW_FP64_PAIRED")) == 0);
+    static const char *tune = getenv("V2R_IDW_TUNE");
     const Variant *fallback = nullptr;
+    if (tune && *tune)
+        for (const Variant &v : kVariants)
+            if (v.tag && !strcmp(v.tag, tune) && v.mode == ps.mode && v.E == ps.count && v.k0 == ps.k0 && v.dk == ps.dk) return &v;
     for (const Variant &v : kVariants) {
+        if (v.tag) continue;
         if (v.paired && !allow_paired) continue;
         if (v.mode != ps.mode || v.E != ps.count) continue;
         if (ps.mode == MODE_GEN) return &v;
@@ -280,7 +292,7 @@ extern "C" int v2r_idw_describe(const double *exps, int n_exps, int precision, c
             if (!v) return set_error(V2R_IDW_EINVAL, "no kernel variant");
             char tmp[160];
             snprintf(tmp, sizeof tmp, "%sfp64/%s E=%d cells=%dx%d k0=%d dk=%d%s", s.empty() ? "" : " + ", mode_name(ps.mode),
-                     ps.count, v->cr, v->cc, ps.k0, ps.dk, v->paired ? " (paired reciprocal)" : (v->k0 ? " (static ladder)" : ""));
+                     ps.count, v->cr, v->cc, ps.k0, ps.dk, v->tag ? v->tag : (v->paired ? " (paired reciprocal)" : (v->k0 ? " (static ladder)" : "")));
             s += tmp;
             ops += model_ops(ps, *v);
         }
