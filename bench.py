@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--band-rows", type=int, default=0, help="rows of the rank's band per step (0 = the whole workload grid)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank keeps one workload-sized band (grid grows with N); strong: the workload's own grid is split into N row bands")
     ap.add_argument("--exps", default="", help="comma list overriding the workload's exponent sweep (diagnostics)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
@@ -185,13 +187,13 @@ def ours(args):
     prec = _lib.FP64 if args.precision == "fp64" else _lib.FP32
 
     # ---- workload: every rank keeps one workload-sized row band (weak scaling) ----------------
-    x, y, w, xi, yi, exps = workloads.make(args.workload, scale_rows=world)
+    from v2r_b200.distributed import shard_rows
+    x, y, w, xi, yi, exps = workloads.make(args.workload, scale_rows=world if args.scaling == "weak" else 1)
     if args.exps:
         exps = np.array([float(v) for v in args.exps.split(",")])
     ps = V.MakeCoordSpace(x, y, w, xi, yi)
     grid = make_grid(xi, yi)
-    band = grid.rows // world
-    row0 = rank * band
+    row0, band = shard_rows(grid.rows, world, rank)      # contiguous row band of this rank
     nrows = band if args.band_rows <= 0 else min(args.band_rows, band)
     n, E = len(ps), len(exps)
 
@@ -253,7 +255,10 @@ def ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    pair_evals_step = float(nrows) * grid.cols * n * world          # all ranks
+    tot_rows = torch.tensor([nrows], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_rows)
+    pair_evals_step = float(tot_rows.item()) * grid.cols * n          # all ranks
     value = pair_evals_step * args.steps / (ms_total * 1e-3) / 1e9
 
     # sanity: the band is finite and exact-hit cells carry their weights (cheap, device side)
@@ -315,9 +320,9 @@ def ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if prec == _lib.FP64 else "f32(tile)/f64(accumulate)",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64" if prec == _lib.FP64 else "f32(tile)/f64(accumulate)",
             "data": "synthetic",
-            "config": {"workload": _workload_name(args.workload, world) + (f" [exps overridden: {args.exps}]" if args.exps else ""),
+            "config": {"workload": _workload_name(args.workload, world if args.scaling == "weak" else 1) + (f" [exps overridden: {args.exps}]" if args.exps else ""),
                        "points_after_dedupe": n, "exponents": E,
                        "rows_per_rank": nrows, "cols": int(grid.cols), "l2": "flushed between timed iterations (256 MiB memset); output band > L2",
                        "parallelism": f"row bands x{world}"},
@@ -344,6 +349,7 @@ def run_e2e(args, V, L, ps, grid, exps_c, prec, world, rank, local, barrier, ban
     if rank == 0:
         ctx = V.IdwContext(n_gpus=world) if world > 1 else V.IdwContext(device=local)
         rows = grid.rows if args.band_rows <= 0 else min(args.band_rows * world, grid.rows)
+        rows = min(rows, grid.rows)
         nbytes_out = E * rows * grid.cols * 8
         pin = C.c_void_p()
         _lib.check(L.v2r_idw_alloc_pinned(nbytes_out, C.byref(pin)))

@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "idw_math.cuh"
+
 namespace v2r {
 
 enum Mode : int {
@@ -160,11 +162,12 @@ __device__ __forceinline__ double base_pow(double d2) {
 template <int MODE, int E, int K0, int DK>
 __device__ __forceinline__ void weights(double d2, const KParams &p, double (&h)[E]) {
     if constexpr (MODE == MODE_GEN) {
-        double L = log2(d2);
+        const double L = fast_log2(d2);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            double c = p.cexp[e];
-            h[e] = (c == 0.0) ? 1.0 : exp2(c * L);  // Go: Pow(d, -0) == 1 even at d == 0
+            const double c = p.cexp[e];
+            // Go: Pow(d, -0) == 1 even at d == 0.  The test is on the integer words (no FP64 compare).
+            h[e] = ((hi_word(c) & 0x7fffffff) | lo_word(c)) == 0 ? 1.0 : fast_exp2(c * L);
         }
     } else {
         double b = base_pow<MODE>(d2);
@@ -191,9 +194,10 @@ __device__ __forceinline__ void weights(double d2, const KParams &p, double (&h)
 // PAIRED (p == 2 only): two points share ONE reciprocal, 1/a + 1/b = (a+b)/(ab) and
 // w0/a + w1/b = (w0 b + w1 a)/(ab): 11 FP64 instructions per two pairs instead of 12, and half the MUFU
 // traffic.  Needs a*b to stay a normal double (squared distances in (1e-154, 1e154)).
-template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS, int MINB, bool PAIRED = false>
+template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS, int MINB, int PAIRED = 0>
 __global__ void __launch_bounds__(THREADS, MINB) idw_fp64_kernel(const __grid_constant__ KParams p) {
     static_assert(!PAIRED || (MODE == MODE_RCP && E == 1 && K0 == 1), "pairing is the p = 2 trick");
+    constexpr int UNR = PAIRED > 1 ? PAIRED : 1;  // PAIRED = unroll factor of the two-point loop
     constexpr int WARPS = THREADS / 32;
     constexpr int T = kTilePoints;
     constexpr int S = kStages;
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, MINB) idw_fp64_kernel(const __grid_co
         const double *sx = sm[s][0], *sy = sm[s][1], *sw = sm[s][2];
         int i = 0;
         if constexpr (PAIRED) {
-#pragma unroll 1
+#pragma unroll UNR
             for (; i + 1 < cnt; i += 2) {
                 const double2 x = *reinterpret_cast<const double2 *>(sx + i);
                 const double2 y = *reinterpret_cast<const double2 *>(sy + i);

@@ -111,13 +111,15 @@ static const Variant kVariants[] = {
     // tuning builds (V2R_IDW_TUNE=<tag>), kept to document what was measured; never picked by default
     V2R_TUNE("t384", MODE_RCP, 1, 4, 4, 1, 0, 384, 1), V2R_TUNE("t384", MODE_QRT, 1, 4, 4, 3, 0, 384, 1),
     V2R_TUNE("b2", MODE_RCP, 1, 4, 2, 1, 0, 256, 2), V2R_TUNE("b2", MODE_QRT, 9, 1, 2, 1, 1, 256, 2),
-    V2R_TUNE("c1x4", MODE_QRT, 9, 1, 4, 1, 1, 256, 1), V2R_TUNE("b2", MODE_QRT, 1, 2, 4, 3, 0, 256, 2),
-    Variant{MODE_RCP, 1, 1, 0, 4, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 4, 4, 1, 0, 256, 1, true>, "MODE_RCP", true, nullptr},  // p = 2, paired (c2, c4)
+    V2R_TUNE("c1x4", MODE_QRT, 9, 1, 4, 1, 1, 256, 1), V2R_TUNE("c4x4", MODE_QRT, 1, 4, 4, 3, 0, 256, 1),
+    Variant{MODE_RCP, 1, 1, 0, 4, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 4, 4, 1, 0, 256, 1, 2>, "MODE_RCP", true, "u2"},
+    Variant{MODE_RCP, 1, 1, 0, 4, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 4, 4, 1, 0, 256, 1, 1>, "MODE_RCP", true, nullptr},  // p = 2, paired (c2, c4)
     V2R_VARIANT(MODE_RCP, 1, 4, 4, 1, 0, 256, 1),   // p = 2, one reciprocal per pair (V2R_IDW_FP64_PAIRED=0)
-    V2R_VARIANT(MODE_RSQ, 1, 4, 4, 1, 0, 256, 1),   // p = 1
-    V2R_VARIANT(MODE_RSQ, 1, 4, 4, 3, 0, 256, 1),   // p = 3
-    V2R_VARIANT(MODE_QRT, 1, 4, 4, 1, 0, 256, 1),   // p = 0.5
-    V2R_VARIANT(MODE_QRT, 1, 4, 4, 3, 0, 256, 1),   // p = 1.5 (the CLI default --es 1.5)
+    // rsqrt / root4 bases have longer dependent chains: 2x4 cells at two CTAs per SM measured +8 % over 4x4 at one
+    V2R_VARIANT(MODE_RSQ, 1, 2, 4, 1, 0, 256, 2),   // p = 1
+    V2R_VARIANT(MODE_RSQ, 1, 2, 4, 3, 0, 256, 2),   // p = 3
+    V2R_VARIANT(MODE_QRT, 1, 2, 4, 1, 0, 256, 2),   // p = 0.5
+    V2R_VARIANT(MODE_QRT, 1, 2, 4, 3, 0, 256, 2),   // p = 1.5 (the CLI default --es 1.5)
     V2R_VARIANT(MODE_QRT, 9, 2, 2, 1, 1, 256, 1),   // p = 0.5 .. 4.5 step 0.5  (config c3)
     V2R_VARIANT(MODE_QRT, 4, 2, 2, 2, 1, 256, 2),   // p = 1, 1.5, 2, 2.5       (config c5)
     // runtime ladders
@@ -169,7 +171,7 @@ static double model_ops(const Pass &ps, const Variant &v) {
         return hi + m - 1;
     };
     if (ps.mode == MODE_GEN) {
-        ops += 30.0 + 25.0 * E;  // software log2 once, exp2 per exponent (approximate)
+        ops += 16.0 + 18.0 * E;  // fast_log2 once (16), c*L + fast_exp2 per exponent (1 + 17)
     } else {
         ops += ps.mode == MODE_RCP ? 3 : (ps.mode == MODE_RSQ ? 5 : 7);
         if (v.paired) ops -= 0.5;  // 11 instead of 12 instructions per two pairs
