@@ -181,8 +181,12 @@ def ours(args):
         raise SystemExit("bench.py needs a CUDA device: v2r_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # host-side barrier for the e2e leg: an NCCL barrier would park a spinning kernel on every other
+        # GPU while rank 0's context drives those same GPUs
+        cpu_group = dist.new_group(backend="gloo")
     L = _lib.load()
     prec = _lib.FP64 if args.precision == "fp64" else _lib.FP32
 
@@ -267,7 +271,11 @@ def ours(args):
     # ---- e2e through the C ABI with host buffers ------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, V, L, ps, grid, exps_c, prec, world, rank, local, barrier, band)
+        def host_barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier(group=cpu_group)
+        e2e = run_e2e(args, V, L, ps, grid, exps_c, prec, world, rank, local, host_barrier, band)
 
     # ---- roofline + peaks + cpu baseline (rank 0) --------------------------------------------------
     if rank == 0:
