@@ -1,0 +1,107 @@
+"""The C++ host (`v2r_b200/bin/v2r idw ...`): same flags as the reference CLI (cmd/idw.go:50-67), readers that
+fill SoA buffers, native BigTIFF sink, TransferType.  CPU tests use --plan (no GPU needed); the GPU tests replay
+features/idw/idw_test.go through the CLI and compare a gpkg sweep with the oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+from v2r_b200 import raster_io, workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+V2R = os.path.join(ROOT, "v2r_b200", "bin", "v2r")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def run(*args, check=True):
+    p = subprocess.run([V2R, *args], capture_output=True, text=True)
+    if check:
+        assert p.returncode == 0, p.stderr
+    return p
+
+
+def test_plan_txt_defaults_match_reference_cli():
+    p = json.loads(run("idw", "-f", os.path.join(GOLDEN, "idw_in.txt"), "--plan", "-e").stdout)
+    # defaults: --es 1.5 --ei .5, ee = es+ei -> one exponent 1.5; --sx/--sy only name the file in txt mode
+    assert (p["rows"], p["cols"], p["points"], p["exponents"]) == (16, 13, 5, 1)
+    assert p["first_outfile"] == "data/idw/idw_in_step100-100pow1.5.tiff" and "root4" in p["kernel"]
+    p = json.loads(run("idw", "--file", os.path.join(GOLDEN, "idw_in.txt"), "--plan", "-e", "-c", "--es=0.5", "--ee", "5",
+                       "--outPath", "out/").stdout)
+    assert p["exponents"] == 9 and p["first_outfile"] == "out/idw_in_step100-100chunkedpow0.5.tiff"
+
+
+def test_plan_gpkg_reader_matches_fixture():
+    p = json.loads(run("idw", "-g", "-f", os.path.join(GOLDEN, "input.gpkg"), "--layer", "wsels", "--field", "elevation",
+                       "--sx", "1", "--sy", "2", "--plan", "-e").stdout)
+    xi, yi = O.Info(1.2020401943588393e+07, 1.2096825067172093e+07, 1.0), O.Info(3.885548111378168e+06, 3.953694544257536e+06, 2.0)
+    assert (p["rows"], p["cols"]) == O.get_dimensions(xi, yi) and p["points"] == 14
+
+
+def test_cli_errors_like_the_reference():
+    f = os.path.join(GOLDEN, "idw_in.txt")
+    assert "has no iterations" in run("idw", "-f", f, "--es", "2", "--ee", "1", check=False).stderr     # cmd/idw.go:86-88
+    assert "must be > 0" in run("idw", "-f", f, "--ei", "0", check=False).stderr                        # cmd/idw.go:83-85
+    assert "\"file\" not set" in run("idw", check=False).stderr
+    assert "\"layer\", \"field\" not set" in run("idw", "-g", "-f", f, check=False).stderr              # cmd/idw.go:71-76
+    p = run("idw", "-g", "-f", os.path.join(GOLDEN, "input.gpkg"), "--layer", "nope", "--field", "elevation", "--plan", check=False)
+    assert p.returncode == 1 and "not in file" in p.stderr                                              # io_gdal.go:134-159
+
+
+def test_translate_matches_python_sink(tmp_path):
+    z = np.random.default_rng(0).normal(0, 50, (16, 13))
+    z[2, 3] = 45.5
+    gd = raster_io.CreateGDalInfo(-1.0, 0.0, 1.0, 1.0, 7, "EPSG:2284")
+    raster_io.WriteGDAL(z, gd, str(tmp_path / "a.tiff"), (0, 0), (16, 13), (16, 13), True)
+    run("translate", str(tmp_path / "a.tiff"), str(tmp_path / "a.asc"), "Int16")
+    assert open(tmp_path / "a.asc", "rb").read() == O.aaigrid_int16_bytes(z, -1.0, 0.0, 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("conc", [False, True])
+def test_golden_through_cli(tmp_path, conc):
+    """features/idw/idw_test.go: pow 1.7, serial and chunked (3x2), GTiff -> Int16 AAIGrid -> golden bytes"""
+    out = str(tmp_path) + "/"
+    args = ["idw", "-f", os.path.join(GOLDEN, "idw_in.txt"), "--es", "1.7", "--ei", "1", "--outPath", out, "-e"]
+    if conc:
+        args += ["-c", "--cy", "3", "--cx", "2"]
+    run(*args)
+    tiff = out + f"idw_in_step100-100{'chunked' if conc else ''}pow1.7.tiff"
+    run("translate", tiff, tiff[:-5] + ".asc", "Int16")
+    assert open(tiff[:-5] + ".asc", "rb").read() == open(os.path.join(GOLDEN, "idw_correct_step1-1.asc"), "rb").read()
+    z, x0, y0, dx, dy = raster_io.ReadTiff(tiff)            # the Python sink reads what the C++ sink wrote
+    assert z.shape == (16, 13) and (x0, y0, dx, dy) == (-1.0, 0.0, 1.0, 1.0)
+
+
+@pytest.mark.gpu
+def test_gpkg_sweep_through_cli_vs_oracle(tmp_path):
+    x, y, w, xi, yi, _ = workloads.make("c2", n_points=3000, cells=96)
+    gp = str(tmp_path / "pts.gpkg")
+    workloads.write_gpkg(gp, x, y, w)
+    out = str(tmp_path) + "/"
+    run("idw", "-g", "-f", gp, "--layer", "wsels", "--field", "elevation", "--sx", "100", "--sy", "100", "--es", "1", "--ee", "3",
+        "--ei", "0.5", "--outPath", out, "-e", "-c", "--cy", "40", "--cx", "40")
+    oxi, oyi = O.Info(float(x.min()), float(x.max()), 100.0), O.Info(float(y.min()), float(y.max()), 100.0)
+    ops = O.make_coord_space(x, y, w, oxi, oyi)
+    for p in (1.0, 1.5, 2.0, 2.5):
+        z = raster_io.ReadTiff(out + f"pts_step100-100chunkedpow{p:.1f}.tiff")[0]
+        ref = O.chunk_solve(ops, oxi, oyi, 8, 32, p)
+        assert z.shape == ref.shape == (96, 96)
+        assert np.max(np.abs(z - ref) / np.abs(ref)) < 1e-12          # weights > 0: scale == |z|
+
+
+@pytest.mark.gpu
+def test_txt_100k_points_through_cli(tmp_path):
+    x, y, w, xi, yi, _ = workloads.make("c2", n_points=100_000, cells=256)
+    f = str(tmp_path / "big.txt")
+    workloads.write_txt(f, x, y, w, xi, yi)
+    out = str(tmp_path) + "/"
+    run("idw", "-f", f, "--es", "2", "--ei", "1", "--outPath", out, "-e", "--fp32")
+    z = raster_io.ReadTiff(out + "big_step100-100pow2.0.tiff")[0]
+    ops = O.make_coord_space(x, y, w, O.Info(xi.min, xi.max, 100.0), O.Info(yi.min, yi.max, 100.0))
+    rr, cc = np.arange(0, 256, 17), np.arange(3, 256, 19)[:16]
+    ref = O.solve_cells(ops, O.Info(xi.min, xi.max, 100.0), O.Info(yi.min, yi.max, 100.0), 2.0, rr[:len(cc)], cc)
+    assert np.max(np.abs(z[rr[:len(cc)], cc] - ref) / np.abs(ref)) < 2e-5
