@@ -333,3 +333,64 @@ def test_fp32_c2_full_size_spot_check(ctx, c2):
     ref = O.solve_cells(o_ps(ps), o_info(xi), o_info(yi), 2.0, rr, cc)
     assert_parity(z[rr, cc], ref, np.abs(ref), rel=REL32, what="fp32 c2 spot check")
     assert np.array_equal(z[ps.key_r, ps.key_c], ps.w)
+
+
+# --------------------------------------------------------------------------- c4 / c5 shapes, randomized sweep
+def test_c4_clustered_full_width_band(ctx):
+    """BASELINE.json config 4 (1 M clustered points -> 16384^2, p = 2): a 32-row full-width band through the
+    paired-reciprocal kernel and the FP32 path, spot-checked against the oracle; dedupe merges clustered points."""
+    x, y, w, xi, yi, exps = workloads.make("c4")
+    ps = V.MakeCoordSpace(x, y, w, xi, yi)
+    ops = O.make_coord_space(x, y, w, o_info(xi), o_info(yi))
+    assert len(ps) == len(ops) < len(x) and np.array_equal(ps.w, ops.w) and np.array_equal(ps.key_c, ops.key_c)
+    grid = make_grid(xi, yi)
+    assert (grid.rows, grid.cols) == (16384, 16384)
+    r0 = 8192
+    z = ctx.solve_rows(ps, grid, r0, 32, exps)[0]
+    z32 = ctx.solve_rows(ps, grid, r0, 32, exps, _lib.FP32)[0]
+    rng = np.random.default_rng(8)
+    rr, cc = r0 + rng.integers(0, 32, 48), rng.integers(0, grid.cols, 48)
+    ref = O.solve_cells(ops, o_info(xi), o_info(yi), 2.0, rr, cc)
+    assert_parity(z[rr - r0, cc], ref, np.abs(ref), what="c4 band")
+    assert_parity(z32[rr - r0, cc], ref, np.abs(ref), rel=REL32, what="c4 band fp32")
+    inband = (ps.key_r >= r0) & (ps.key_r < r0 + 32)
+    assert inband.sum() > 0 and np.array_equal(z[ps.key_r[inband] - r0, ps.key_c[inband]], ps.w[inband])
+
+
+def test_c5_epsg2284_sweep_band(ctx):
+    """BASELINE.json config 5 shape (EPSG:2284 offsets 1.1e7 / 3e6, 32768 columns, p = 1, 1.5, 2, 2.5) with
+    200 k of its points: a 16-row full-width band, all four exponents from one pass."""
+    x, y, w, xi, yi, exps = workloads.make("c5", n_points=200_000)
+    ps = V.MakeCoordSpace(x, y, w, xi, yi)
+    grid = make_grid(xi, yi)
+    assert (grid.rows, grid.cols) == (32768, 32768) and exps.tolist() == [1.0, 1.5, 2.0, 2.5]
+    r0 = 20000
+    z = ctx.solve_rows(ps, grid, r0, 16, exps)
+    rng = np.random.default_rng(9)
+    rr, cc = r0 + rng.integers(0, 16, 32), rng.integers(0, grid.cols, 32)
+    for e, p in enumerate(exps):
+        ref = O.solve_cells(o_ps(ps), o_info(xi), o_info(yi), float(p), rr, cc)
+        assert_parity(z[e][rr - r0, cc], ref, np.abs(ref), what=f"c5 p={p}")
+
+
+def test_randomized_grids_points_and_sweeps(ctx):
+    """40 random problems: grid shape, step, origin magnitude, point count, signed weights, sweep (es, ee, ei)."""
+    rng = np.random.default_rng(2024)
+    for it in range(40):
+        rows, cols = int(rng.integers(1, 90)), int(rng.integers(1, 200))
+        step = float(rng.choice([0.25, 1.0, 3.0, 100.0]))
+        x0, y0 = float(rng.choice([0.0, -500.0, 1.2e7])), float(rng.choice([0.0, 3.9e6]))
+        n = int(rng.integers(1, 1400))
+        xi, yi = V.Info(x0, x0 + cols * step - 1, step), V.Info(y0, y0 + rows * step - 1, step)
+        rows, cols = V.GetDimensions(xi, yi)
+        if rows < 1 or cols < 1:
+            continue
+        ps = V.MakeCoordSpace(rng.uniform(x0 - step, x0 + (cols + 1) * step, n), rng.uniform(y0 - step, y0 + (rows + 1) * step, n),
+                              rng.normal(0, 100, n), xi, yi)
+        es = float(rng.choice([0.5, 1.0, 1.5, 2.0, 0.7, 3.0]))
+        ei = float(rng.choice([0.5, 1.0, 0.3, 2.0]))
+        exps = V.exp_range(es, es + ei * int(rng.integers(1, 5)) - 1e-9, ei)
+        zs = V.solve(ps, xi, yi, exps, ctx=ctx)
+        for e, p in enumerate(exps):
+            ref, scale = oracle_ref(ps, xi, yi, float(p))
+            assert_parity(zs[e], ref, scale, what=f"random #{it} {rows}x{cols} n={n} step={step} p={p}")

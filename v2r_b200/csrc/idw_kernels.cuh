@@ -126,16 +126,16 @@ __device__ __forceinline__ double pow_m14(double a) {
     return fma(qe, p, q0);
 }
 
+// b^K as a balanced product b^(K/2) * b^(K - K/2): depth log2 K instead of K.  In a sweep every exponent calls
+// this with its own K; the common sub-powers are merged by the compiler (pure FP multiplies of identical
+// operands), so consecutive powers 1..9 still cost 8 multiplies but the dependent chain is 4 deep, not 8.
 template <int K>
 __device__ __forceinline__ double ipow_c(double b) {
     static_assert(K >= 1, "power must be positive");
     if constexpr (K == 1) {
         return b;
-    } else if constexpr (K % 2 == 0) {
-        double h = ipow_c<K / 2>(b);
-        return h * h;
     } else {
-        return ipow_c<K - 1>(b) * b;
+        return ipow_c<K / 2>(b) * ipow_c<K - K / 2>(b);
     }
 }
 // runtime (warp-uniform) power, k >= 1
@@ -158,6 +158,14 @@ __device__ __forceinline__ double base_pow(double d2) {
     else return pow_m14(d2);
 }
 
+template <int E, int K0, int DK, int I>
+__device__ __forceinline__ void static_powers(double b, double (&h)[E]) {
+    if constexpr (I < E) {
+        h[I] = ipow_c<K0 + I * DK>(b);
+        static_powers<E, K0, DK, I + 1>(b, h);
+    }
+}
+
 // h[e] = d2^(-p_e/2) for all exponents of the pass.
 template <int MODE, int E, int K0, int DK>
 __device__ __forceinline__ void weights(double d2, const KParams &p, double (&h)[E]) {
@@ -172,19 +180,14 @@ __device__ __forceinline__ void weights(double d2, const KParams &p, double (&h)
     } else {
         double b = base_pow<MODE>(d2);
         if constexpr (K0 > 0) {
-            h[0] = ipow_c<K0>(b);
+            static_powers<E, K0, (DK > 0 ? DK : 1), 0>(b, h);
         } else {
             h[0] = ipow_rt(b, p.k0);
-        }
-        if constexpr (E > 1) {
-            double m;
-            if constexpr (K0 > 0) {
-                m = ipow_c<(DK > 0 ? DK : 1)>(b);
-            } else {
-                m = ipow_rt(b, p.dk);
-            }
+            if constexpr (E > 1) {
+                const double m = ipow_rt(b, p.dk);
 #pragma unroll
-            for (int e = 1; e < E; ++e) h[e] = h[e - 1] * m;
+                for (int e = 1; e < E; ++e) h[e] = h[e - 1] * m;
+            }
         }
     }
 }
