@@ -40,9 +40,12 @@ def o_ps(ps):
 def oracle_ref(ps, xi, yi, p, rows=None, cols=None):
     """(reference raster, tolerance scale sum|w|h/sum h) from the threaded oracle (bit-identical to its
     serial FullSolve, tests/test_oracle_golden.py); the scale is the same IDW run on |w|."""
-    ref = O.chunk_solve(o_ps(ps), o_info(xi), o_info(yi), 8, 64, p, rows, cols)
+    if rows is None:
+        rows, cols = O.get_dimensions(o_info(xi), o_info(yi))
+    cr, cc = max(1, min(8, rows)), max(1, min(64, cols))      # (an oversize chunk makes ChunkSolve quarter the grid)
+    ref = O.chunk_solve(o_ps(ps), o_info(xi), o_info(yi), cr, cc, p, rows, cols)
     absw = O.PointSet(ps.x, ps.y, np.abs(ps.w), ps.key_r, ps.key_c)
-    scale = O.chunk_solve(absw, o_info(xi), o_info(yi), 8, 64, p, rows, cols)
+    scale = O.chunk_solve(absw, o_info(xi), o_info(yi), cr, cc, p, rows, cols)
     return ref, scale
 
 
