@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -257,13 +258,14 @@ static int upload_points(v2r_idw_ctx *ctx, const double *x, const double *y, con
         CUDA_TRY(cudaMemcpyAsync(d0.d_kc, kc, n * 8, cudaMemcpyHostToDevice, d0.compute));
     }
     if (ctx->dev.size() > 1 && n > 0) {
-        for (int a = 0; a < 5; ++a) {
+        auto arrays = [](DeviceState &d) { return std::array<void *, 5>{d.d_x, d.d_y, d.d_z, d.d_kr, d.d_kc}; };
+        const std::array<void *, 5> src = arrays(d0);
+        for (int a = 0; a < 5; ++a) {  // one grouped broadcast per array: x, y, z (float64), key_r, key_c (int64)
             NCCL_TRY(g_nccl.GroupStart());
             for (auto &d : ctx->dev) {
-                void *src = a == 0 ? (void *)d0.d_x : a == 1 ? (void *)d0.d_y : a == 2 ? (void *)d0.d_z : a == 3 ? (void *)d0.d_kr : (void *)d0.d_kc;
-                void *dst = a == 0 ? (void *)d.d_x : a == 1 ? (void *)d.d_y : a == 2 ? (void *)d.d_z : a == 3 ? (void *)d.d_kr : (void *)d.d_kc;
-                // root's sendbuff is its own array; non-roots pass their receive buffer for both
-                NCCL_TRY(g_nccl.Broadcast(&d == &d0 ? src : dst, dst, (size_t)n, a < 3 ? ncclDouble : ncclInt64, 0, d.comm, d.compute));
+                void *dst = arrays(d)[a];
+                // the root sends its own array; the other ranks pass their receive buffer for both arguments
+                NCCL_TRY(g_nccl.Broadcast(&d == &d0 ? src[a] : dst, dst, (size_t)n, a < 3 ? ncclDouble : ncclInt64, 0, d.comm, d.compute));
             }
             NCCL_TRY(g_nccl.GroupEnd());
         }
@@ -307,7 +309,7 @@ static int begin_session(v2r_idw_ctx *ctx, const double *x, const double *y, con
                          const int64_t *kc, long long n, const v2r_idw_grid *grid, long long row0, long long nrows,
                          const double *exps, int n_exps, int precision, long long band_rows) {
     if (ctx->ses.active) return set_error(V2R_IDW_ESTATE, "a streaming session is already open on this context");
-    int rc = validate_launch((const void *)16, (const void *)16, (const void *)16, n, grid, row0, nrows, n_exps, (const void *)16);
+    int rc = validate_geometry(n, grid, row0, nrows, n_exps);
     if (rc) return rc;
     if (n > 0 && (!x || !y || !z || !kr || !kc)) return set_error(V2R_IDW_EINVAL, "point or key arrays are NULL");
     if (precision != V2R_IDW_FP64 && precision != V2R_IDW_FP32) return set_error(V2R_IDW_EINVAL, "unknown precision %d", precision);

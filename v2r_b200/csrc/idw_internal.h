@@ -23,6 +23,7 @@ int set_error(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3
 const char *last_error();
 
 int plan_sweep(const double *exps, int n_exps, std::vector<Pass> &passes);
+int validate_geometry(long long n, const v2r_idw_grid *g, long long row0, long long nrows, int n_exps);
 int validate_launch(const void *d_x, const void *d_y, const void *d_z, long long n, const v2r_idw_grid *g,
                     long long row0, long long nrows, int n_exps, const void *d_out);
 int launch_rows_fp64(cudaStream_t stream, const double *d_x, const double *d_y, const double *d_z,

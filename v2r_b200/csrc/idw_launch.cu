@@ -244,15 +244,21 @@ int launch_rows_fp64(cudaStream_t stream, const double *d_x, const double *d_y, 
     return launch_patch_exact(stream, d_z, d_kr, d_kc, n, g, row0, nrows, d_out, n_exps);
 }
 
-int validate_launch(const void *d_x, const void *d_y, const void *d_z, long long n, const v2r_idw_grid *g,
-                    long long row0, long long nrows, int n_exps, const void *d_out) {
+int validate_geometry(long long n, const v2r_idw_grid *g, long long row0, long long nrows, int n_exps) {
     if (!g) return set_error(V2R_IDW_EINVAL, "grid is NULL");
     if (n < 0) return set_error(V2R_IDW_EINVAL, "n < 0");
-    if (n > 0 && (!d_x || !d_y || !d_z)) return set_error(V2R_IDW_EINVAL, "point arrays are NULL");
     if (g->rows < 0 || g->cols < 0) return set_error(V2R_IDW_EINVAL, "negative grid dimensions");
     if (row0 < 0 || nrows < 0 || row0 + nrows > g->rows)
         return set_error(V2R_IDW_EINVAL, "rows [%lld, %lld) outside the grid of %lld rows", row0, row0 + nrows, (long long)g->rows);
     if (n_exps < 1 || n_exps > 64) return set_error(V2R_IDW_EINVAL, "n_exps must be in [1, 64]");
+    return V2R_IDW_OK;
+}
+
+int validate_launch(const void *d_x, const void *d_y, const void *d_z, long long n, const v2r_idw_grid *g,
+                    long long row0, long long nrows, int n_exps, const void *d_out) {
+    int rc = validate_geometry(n, g, row0, nrows, n_exps);
+    if (rc) return rc;
+    if (n > 0 && (!d_x || !d_y || !d_z)) return set_error(V2R_IDW_EINVAL, "point arrays are NULL");
     if (nrows > 0 && g->cols > 0 && !d_out) return set_error(V2R_IDW_EINVAL, "out is NULL");
     if (((uintptr_t)d_x | (uintptr_t)d_y | (uintptr_t)d_z) & 15)
         return set_error(V2R_IDW_EINVAL, "device point arrays must be 16-byte aligned (TMA bulk copies)");
