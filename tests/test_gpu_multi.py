@@ -38,3 +38,47 @@ def test_single_process_multi_gpu_equals_single_gpu(n_gpus):
         sub = cn.solve_rows(ps, grid, 100, 333, exps)               # ragged sub-range over N devices
         assert np.array_equal(sub, want[:, 100:433])
         assert cn.last_timing()["kernel_ms"] > 0
+
+
+_TORCHRUN_SCRIPT = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["V2R_ROOT"])
+import v2r_b200 as V
+from v2r_b200.distributed import solve_distributed
+from v2r_b200.idw import make_grid
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+xi, yi = V.Info(0, 199, 1.0), V.Info(0, 611, 1.0)
+grid = make_grid(xi, yi)
+exps = np.array([0.5, 1.0, 1.5, 2.0, 2.5])
+ps = None
+if rank == 0:                       # only rank 0 owns the points, like the Go host
+    rng = np.random.default_rng(12)
+    ps = V.MakeCoordSpace(rng.uniform(0, 200, 4000), rng.uniform(0, 612, 4000), rng.normal(0, 30, 4000), xi, yi)
+full = solve_distributed(ps, grid, exps)
+if rank == 0:
+    with V.IdwContext(device=0) as c:
+        want = c.solve(ps, grid, exps)
+    assert np.array_equal(full.cpu().numpy(), want), "row-band sharded raster differs from the single-GPU raster"
+    print("DIST_OK")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_torchrun_row_bands_over_nccl(tmp_path):
+    """one process per GPU (v2r_b200/distributed.py): NCCL broadcast of the points, v2r_idw_launch_rows per band,
+    point-to-point gather to rank 0 -- bit-equal to the single-GPU raster"""
+    import os
+    import subprocess
+    import sys
+    n = min(_ngpu(), 4)
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "dist_check.py"
+    script.write_text(_TORCHRUN_SCRIPT)
+    env = dict(os.environ, V2R_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0 and "DIST_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-3000:]

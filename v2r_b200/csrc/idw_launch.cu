@@ -100,7 +100,7 @@ struct Variant {
 
 // Cell block per thread shrinks as E grows (2*E*CR*CC FP64 accumulators live in registers).
 #define V2R_ROW(MODE)                                                                                  \
-    V2R_VARIANT(MODE, 1, 4, 4, 0, 0, 256, 1), V2R_VARIANT(MODE, 2, 2, 4, 0, 0, 256, 1),                \
+    V2R_VARIANT(MODE, 1, 2, 4, 0, 0, 256, 2), V2R_VARIANT(MODE, 2, 2, 4, 0, 0, 256, 1),                \
         V2R_VARIANT(MODE, 3, 2, 2, 0, 0, 256, 2), V2R_VARIANT(MODE, 4, 2, 2, 0, 0, 256, 2),            \
         V2R_VARIANT(MODE, 5, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE, 6, 2, 2, 0, 0, 256, 1),            \
         V2R_VARIANT(MODE, 7, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE, 8, 2, 2, 0, 0, 256, 1),            \
