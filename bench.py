@@ -232,7 +232,7 @@ def ours(args):
     # enough to bring clocks, caches and the instruction cache to steady state
     full_nrows = nrows
     if args.workload != "c2":
-        nrows = min(nrows, 512)
+        nrows = min(nrows, 512 if n * E < 3_000_000 else 64)
     for _ in range(max(args.warmup, 3)):
         step()
         flush.zero_()

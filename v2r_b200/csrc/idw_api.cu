@@ -10,7 +10,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
-#include <unordered_map>
 #include <vector>
 
 #include <nccl.h>  // types and prototypes only; the library is dlopen'ed when n_gpus > 1
@@ -549,20 +548,8 @@ int v2r_idw_exp_range(double es, double ee, double ei, double *out, int64_t max_
     return V2R_IDW_OK;
 }
 
-struct PairKey {
-    int64_t r, c;
-    bool operator==(const PairKey &o) const { return r == o.r && c == o.c; }
-};
-struct PairHash {
-    size_t operator()(const PairKey &k) const {
-        uint64_t h = (uint64_t)k.r * 0x9E3779B97F4A7C15ull + (uint64_t)k.c;
-        h ^= h >> 31;
-        h *= 0xD6E8FEB86659FD93ull;
-        h ^= h >> 32;
-        return (size_t)h;
-    }
-};
-
+// tools/utils.go:97-119 with the arrival order fixed to input order.  The Go map becomes a flat
+// open-addressing table (linear probing, load <= 1/2) from key to output slot: 2 M points take ~0.1 s.
 int v2r_idw_make_coord_space(int64_t n, const double *x, const double *y, const double *z, double x_min,
                              double x_step, double y_min, double y_step, double *ox, double *oy, double *oz,
                              int64_t *okr, int64_t *okc, int64_t *n_out) {
@@ -570,32 +557,38 @@ int v2r_idw_make_coord_space(int64_t n, const double *x, const double *y, const 
     *n_out = 0;
     if (n < 0) return set_error(V2R_IDW_EINVAL, "n < 0");
     if (n > 0 && (!x || !y || !z || !ox || !oy || !oz || !okr || !okc)) return set_error(V2R_IDW_EINVAL, "NULL array");
+    uint64_t cap = 16;
+    while (cap < (uint64_t)n * 2 + 1) cap <<= 1;
+    std::vector<int64_t> slot;
     try {
-        std::unordered_map<PairKey, int64_t, PairHash> seen;
-        seen.reserve((size_t)n * 2);
-        int64_t cnt = 0;
-        for (int64_t i = 0; i < n; ++i) {
-            PairKey k{go_int((y[i] - y_min) / y_step), go_int((x[i] - x_min) / x_step)};
-            auto it = seen.find(k);
-            double w = z[i];
-            int64_t slot;
-            if (it != seen.end()) {
-                slot = it->second;
-                w = (w + oz[slot]) / 2;  // tools/utils.go:111: newElev := (p.Weight + elev.Weight) / 2
-            } else {
-                slot = cnt++;
-                seen.emplace(k, slot);
-                okr[slot] = k.r;
-                okc[slot] = k.c;
-            }
-            ox[slot] = x[i];  // position of the last arrival is kept (tools/utils.go:115)
-            oy[slot] = y[i];
-            oz[slot] = w;
-        }
-        *n_out = cnt;
+        slot.assign(cap, -1);
     } catch (const std::bad_alloc &) {
         return set_error(V2R_IDW_ENOMEM, "out of host memory in make_coord_space");
     }
+    const uint64_t mask = cap - 1;
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t r = go_int((y[i] - y_min) / y_step), c = go_int((x[i] - x_min) / x_step);
+        uint64_t h = (uint64_t)r * 0x9E3779B97F4A7C15ull + (uint64_t)c * 0xC2B2AE3D27D4EB4Full;
+        h ^= h >> 29;
+        h *= 0xBF58476D1CE4E5B9ull;
+        h ^= h >> 32;
+        uint64_t j = h & mask;
+        while (slot[j] >= 0 && !(okr[slot[j]] == r && okc[slot[j]] == c)) j = (j + 1) & mask;
+        double w = z[i];
+        int64_t s = slot[j];
+        if (s >= 0) {
+            w = (w + oz[s]) / 2;  // tools/utils.go:111: newElev := (p.Weight + elev.Weight) / 2
+        } else {
+            s = slot[j] = cnt++;
+            okr[s] = r;
+            okc[s] = c;
+        }
+        ox[s] = x[i];  // position of the last arrival is kept (tools/utils.go:115)
+        oy[s] = y[i];
+        oz[s] = w;
+    }
+    *n_out = cnt;
     return V2R_IDW_OK;
 }
 

@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -25,58 +26,104 @@
 namespace v2r {
 namespace processing {
 
-static std::vector<std::string> fields(const std::string &line) {  // strings.Fields
-    std::vector<std::string> f;
-    std::istringstream is(line);
-    std::string t;
-    while (is >> t) f.push_back(t);
-    return f;
+// ---- txt tokenizer ---------------------------------------------------------------------------------
+// The whole file is read once and scanned in place (std::from_chars, ~25 ns per number); the reference's
+// bufio.Scanner + strings.Fields + strconv.ParseFloat per line is what this replaces.
+namespace {
+struct Line { const char *b, *e; };
+struct Tok { const char *b, *e; };
+
+inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+
+// next whitespace-separated token of [p, e)
+inline bool next_tok(const char *&p, const char *e, Tok &t) {
+    while (p < e && is_space(*p)) ++p;
+    if (p >= e) return false;
+    t.b = p;
+    while (p < e && !is_space(*p)) ++p;
+    t.e = p;
+    return true;
 }
-static double parse_float(const std::string &s) {  // strconv.ParseFloat with the error dropped (-> 0)
+// strconv.ParseFloat: ok == false on a syntax error (the reference then uses 0 for points, fails for STEP/ESTIMATE)
+inline double parse_float(Tok t, bool &ok) {
+    const char *b = t.b;
+    if (b < t.e && *b == '+') ++b;
+    double v = 0;
+    auto r = std::from_chars(b, t.e, v);
+    if (r.ec == std::errc() && r.ptr == t.e) { ok = true; return v; }
+    std::string s(t.b, t.e);  // rare spellings (hex floats, "Infinity", out-of-range): let strtod decide
     char *end = nullptr;
-    double v = strtod(s.c_str(), &end);
-    return (end && *end == 0 && end != s.c_str()) ? v : 0.0;
+    v = strtod(s.c_str(), &end);
+    ok = end && *end == 0 && end != s.c_str();
+    return ok ? v : 0.0;
 }
-static double parse_float_strict(const std::string &s, const std::string &file) {
-    char *end = nullptr;
-    double v = strtod(s.c_str(), &end);
-    if (!(end && *end == 0 && end != s.c_str())) throw Error(file + ": strconv.ParseFloat: parsing \"" + s + "\": invalid syntax");
+inline double parse_strict(Tok t, const std::string &file) {
+    bool ok;
+    double v = parse_float(t, ok);
+    if (!ok) throw Error(file + ": strconv.ParseFloat: parsing \"" + std::string(t.b, t.e) + "\": invalid syntax");
     return v;
 }
+}  // namespace
 
 ReadResult ReadTextData(const std::string &filepath, int epsg) {
-    std::ifstream in(filepath);
-    if (!in) throw Error("open " + filepath + ": no such file or directory");
+    std::string buf;
+    {
+        std::ifstream in(filepath, std::ios::binary);
+        if (!in) throw Error("open " + filepath + ": no such file or directory");
+        in.seekg(0, std::ios::end);
+        buf.resize((size_t)in.tellg());
+        in.seekg(0);
+        in.read(&buf[0], (std::streamsize)buf.size());
+    }
     ReadResult r;
     r.points = tools::PointSet(1024);
     r.proj = "EPSG:" + std::to_string(epsg);  // the reference asks GDAL for the WKT of the code (read_data.go:25-34)
-    std::string line;
-    auto next_fields = [&](size_t want) {
-        if (!std::getline(in, line)) line.clear();
-        auto f = fields(line);
-        if (f.size() < want) throw Error(filepath + ": line has fewer than " + std::to_string(want) + " fields (the reference panics: index out of range)");
-        return f;
+    const char *p = buf.data(), *end = buf.data() + buf.size();
+    auto next_line = [&](Line &l) {  // bufio.Scanner: lines split at \n, no token for a trailing empty line
+        if (p >= end) return false;
+        l.b = p;
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+        l.e = nl ? nl : end;
+        p = nl ? nl + 1 : end;
+        return true;
     };
-    while (std::getline(in, line)) {
-        auto f = fields(line);
-        if (f.empty()) throw Error(filepath + ": blank line (the reference panics at read_data.go:40)");
-        if (f[0] == "POINTS") {
-            std::string rest = line.rfind("POINTS ", 0) == 0 ? line.substr(7) : line;
-            long n = strtol(rest.c_str(), nullptr, 10);  // Atoi error dropped -> 0
+    Line l;
+    while (next_line(l)) {
+        const char *q = l.b;
+        Tok head;
+        if (!next_tok(q, l.e, head)) throw Error(filepath + ": blank line (the reference panics at read_data.go:40)");
+        const size_t hl = (size_t)(head.e - head.b);
+        if (hl == 6 && !memcmp(head.b, "POINTS", 6)) {
+            // strconv.Atoi(strings.TrimSpace(strings.TrimPrefix(line, "POINTS "))), error dropped -> 0
+            const char *c = (l.e - l.b >= 7 && !memcmp(l.b, "POINTS ", 7)) ? l.b + 7 : l.b;
+            long n = strtol(std::string(c, l.e).c_str(), nullptr, 10);
             for (long i = 0; i < n; ++i) {
-                auto p = next_fields(3);
-                r.points.push_back(parse_float(p[0]), parse_float(p[1]), parse_float(p[2]));
+                Line pl;
+                if (!next_line(pl)) pl.b = pl.e = end;
+                const char *s = pl.b;
+                Tok t[3];
+                for (int k = 0; k < 3; ++k)
+                    if (!next_tok(s, pl.e, t[k]))
+                        throw Error(filepath + ": point line has fewer than 3 fields (the reference panics: index out of range)");
+                bool ok;
+                r.points.push_back(parse_float(t[0], ok), parse_float(t[1], ok), parse_float(t[2], ok));
             }
-        } else if (f[0] == "STEP") {
-            auto s = next_fields(2);
-            r.xInfo.Step = parse_float_strict(s[0], filepath);
-            r.yInfo.Step = parse_float_strict(s[1], filepath);
-        } else if (f[0] == "ESTIMATE") {
+        } else if (hl == 4 && !memcmp(head.b, "STEP", 4)) {
+            Line sl;
+            if (!next_line(sl)) sl.b = sl.e = end;
+            const char *s = sl.b;
+            Tok a, b2;
+            if (!next_tok(s, sl.e, a) || !next_tok(s, sl.e, b2)) throw Error(filepath + ": STEP needs two numbers");
+            r.xInfo.Step = parse_strict(a, filepath);
+            r.yInfo.Step = parse_strict(b2, filepath);
+        } else if (hl == 8 && !memcmp(head.b, "ESTIMATE", 8)) {
             for (int xy = 0; xy < 2; ++xy) {
-                if (!std::getline(in, line)) line.clear();
-                auto v = fields(line);
-                for (size_t k = 0; k < v.size(); ++k) {
-                    double val = parse_float_strict(v[k], filepath);
+                Line el;
+                if (!next_line(el)) el.b = el.e = end;
+                const char *s = el.b;
+                Tok t;
+                for (int k = 0; next_tok(s, el.e, t); ++k) {
+                    double val = parse_strict(t, filepath);
                     if (xy == 0 && k == 0) r.xInfo.Min = val;
                     if (xy == 0 && k == 1) r.xInfo.Max = val;
                     if (xy == 1 && k == 0) r.yInfo.Min = val;
