@@ -1,0 +1,26 @@
+"""Accuracy of the software log2/exp2 behind the `general` exponent class (v2r_b200/csrc/idw_math.cuh), checked on
+the CPU: the header is __host__ __device__, so nvcc builds it into a host program that compares 2 M samples over
+60 decades with long-double libm, plus every special value the kernels rely on (d2 = 0 -> -inf -> h = +inf -> NaN
+cell; saturation to 0 / +inf; NaN passes through)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_fast_log2_exp2_accuracy_and_specials(tmp_path):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "check_idw_math")
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "v2r_b200", "csrc"),
+                           "-o", exe, os.path.join(ROOT, "tests", "native", "check_idw_math.cu")])
+    out = subprocess.check_output([exe], text=True).split()
+    max_abs_log2, max_rel_exp2, max_rel_pow, bad = float(out[0]), float(out[1]), float(out[2]), int(out[3])
+    assert bad == 0
+    assert max_abs_log2 < 2e-14         # |log2| <= 100 here: that is <= 1.5 ulp of the result
+    assert max_rel_exp2 < 1e-15
+    assert max_rel_pow < 1e-13          # d2^(-p/2) for p < 10 over 60 decades; the parity bar is 1e-12

@@ -16,6 +16,20 @@
 
 namespace v2r {
 
+// Polynomial coefficients live in the constant bank on the device: an FP64 instruction can take a c[bank][off]
+// operand directly, whereas 64-bit literals were being rebuilt with two UMOVs per use (71 per loop iteration,
+// which made the general-class kernel issue-bound).
+#ifdef __CUDA_ARCH__
+#define V2R_COEF __constant__
+#else
+#define V2R_COEF static const
+#endif
+V2R_COEF double kLg[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+                          1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01};  // Lg1..Lg7, FDLIBM e_log.c
+V2R_COEF double kEx[9] = {2.7557319223985893e-07, 2.7557319223985888e-06, 2.4801587301587302e-05, 1.9841269841269841e-04,
+                          1.3888888888888889e-03, 8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};  // 1/10! .. 1/2!
+V2R_COEF double kMisc[3] = {1.4426950408889634074, 6755399441055744.0, 0.34657359027997265471};  // log2(e), 1.5*2^52, ln(2)/2
+
 __host__ __device__ __forceinline__ int hi_word(double a) {
 #ifdef __CUDA_ARCH__
     return __double2hiint(a);
@@ -71,16 +85,16 @@ __host__ __device__ __forceinline__ double fast_log2(double a) {
     r = fma(r, e2, r);
     const double s = f * r;
     const double z = s * s;
-    double p = 1.479819860511658591e-01;      // Lg7 .. Lg1 of FDLIBM e_log.c
-    p = fma(p, z, 1.531383769920937332e-01);
-    p = fma(p, z, 1.818357216161805012e-01);
-    p = fma(p, z, 2.222219843214978396e-01);
-    p = fma(p, z, 2.857142874366239149e-01);
-    p = fma(p, z, 3.999999999940941908e-01);
-    p = fma(p, z, 6.666666666666735130e-01);
+    double p = kLg[6];                        // Lg7 .. Lg1
+    p = fma(p, z, kLg[5]);
+    p = fma(p, z, kLg[4]);
+    p = fma(p, z, kLg[3]);
+    p = fma(p, z, kLg[2]);
+    p = fma(p, z, kLg[1]);
+    p = fma(p, z, kLg[0]);
     const double q = p * z;                   // log(m) = 2s + s*q
     const double lm = fma(s, q, s + s);
-    double L = fma(lm, 1.4426950408889634074, int2double(k));
+    double L = fma(lm, kMisc[0], int2double(k));
     // specials by integer tests only
     if (hi < 0x00100000) L = make_double((int)0xfff00000, 0);             // zero / subnormal -> -inf
     if (hi >= 0x7ff00000) L = a;                                          // +inf / NaN pass through
@@ -95,20 +109,14 @@ __host__ __device__ __forceinline__ double fast_exp2(double t) {
     // stays exact and both halves of 2^n keep a normal exponent field; NaN is left alone
     if (ahi >= 0x409fe000 && (ahi < 0x7ff00000 || (ahi == 0x7ff00000 && lo_word(t) == 0)))
         t = make_double((hi & (int)0x80000000) | 0x409fe000, 0);
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds t to the nearest integer
+    const double magic = kMisc[1];            // 1.5 * 2^52: adding it rounds t to the nearest integer
     const double tn = t + magic;
     const int n = lo_word(tn);                // integer part (two's complement in the low word)
     const double f = t - (tn - magic);        // in [-1/2, 1/2]
-    const double x = f * 0.34657359027997265471;  // (ln 2)/2 * f : exp(x)^2 = 2^f, |x| <= 0.1733
-    double p = 2.7557319223985893e-07;        // 1/10!
-    p = fma(p, x, 2.7557319223985888e-06);    // 1/9!
-    p = fma(p, x, 2.4801587301587302e-05);    // 1/8!
-    p = fma(p, x, 1.9841269841269841e-04);    // 1/7!
-    p = fma(p, x, 1.3888888888888889e-03);    // 1/6!
-    p = fma(p, x, 8.3333333333333332e-03);    // 1/5!
-    p = fma(p, x, 4.1666666666666664e-02);    // 1/4!
-    p = fma(p, x, 1.6666666666666666e-01);    // 1/3!
-    p = fma(p, x, 0.5);
+    const double x = f * kMisc[2];            // (ln 2)/2 * f : exp(x)^2 = 2^f, |x| <= 0.1733
+    double p = kEx[0];                        // Taylor 1/10! .. 1/2!
+#pragma unroll
+    for (int i = 1; i < 9; ++i) p = fma(p, x, kEx[i]);
     p = fma(p, x, 1.0);
     p = fma(p, x, 1.0);
     p = p * p;
