@@ -174,8 +174,12 @@ __device__ __forceinline__ void weights(double d2, const KParams &p, double (&h)
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const double c = p.cexp[e];
-            // Go: Pow(d, -0) == 1 even at d == 0.  The test is on the integer words (no FP64 compare).
-            h[e] = ((hi_word(c) & 0x7fffffff) | lo_word(c)) == 0 ? 1.0 : fast_exp2(c * L);
+            // Go: Pow(d, -0) == 1 even at d == 0 (where c*L would be 0*inf).  The zero test is on the integer words
+            // and only replaces the ARGUMENT: exp2(0) is exactly 1, and keeping fast_exp2 unconditional keeps all
+            // cells' chains in one basic block (a branch per cell serialised them: 17 dependent FP64 ops each).
+            double t = c * L;
+            if (((hi_word(c) & 0x7fffffff) | lo_word(c)) == 0) t = 0.0;
+            h[e] = fast_exp2(t);
         }
     } else {
         double b = base_pow<MODE>(d2);
