@@ -117,7 +117,9 @@ struct Session {
     long long row0 = 0, nrows = 0;  // requested row range
     std::vector<double> exps;
     int precision = 0;
-    long long sub_rows = 0;   // rows per device per round
+    long long sub_rows = 0;   // rows per device per round = one kernel launch (the launch granule)
+    long long slice_rows = 0; // rows handed to the caller per _next call (<= sub_rows): the write granule
+    long long slice_off = 0;  // rows of the current (round, device) band already delivered
     long long rounds = 0;
     long long cur_round = 0;
     int cur_dev = 0;
@@ -336,11 +338,21 @@ static int begin_session(v2r_idw_ctx *ctx, const double *x, const double *y, con
         d.band_rows = e - a;
         d.kernel_ms = 0;
     }
-    // rows per device per round: keep one round of one device under ~1 GiB of output
+    // Launch granule (rows per device per round): at most ~1 GiB of output, and -- when the caller asks for
+    // small bands (the reference's default chunk is 200 rows) -- a multiple of the requested height that still
+    // gives the kernel >= ~16 waves of CTAs, so the WRITE granule of ChunkSolve does not starve the GPU.
     const long long row_bytes = std::max<long long>(1, grid->cols) * 8 * n_exps;
-    long long sub = band_rows > 0 ? band_rows : std::max<long long>(32, ((1LL << 30) / row_bytes) / 32 * 32);
+    const long long cap_rows = std::max<long long>(32, ((1LL << 30) / row_bytes) / 32 * 32);
+    long long sub = cap_rows;
+    if (band_rows > 0) {
+        const long long want_rows = ceil_div(10000000LL, std::max<long long>(1, grid->cols));  // ~1e7 cells per launch
+        const long long k = std::max<long long>(1, std::min(ceil_div(want_rows, band_rows), std::max<long long>(1, cap_rows / band_rows)));
+        sub = band_rows * k;
+    }
     sub = std::min(sub, std::max<long long>(per, 1));
     s.sub_rows = std::max<long long>(sub, 1);
+    s.slice_rows = band_rows > 0 ? std::min<long long>(band_rows, s.sub_rows) : s.sub_rows;
+    s.slice_off = 0;
     s.rounds = per > 0 ? ceil_div(per, s.sub_rows) : 0;
 
     const size_t band_doubles = (size_t)s.sub_rows * (size_t)std::max<long long>(grid->cols, 1) * (size_t)n_exps;
@@ -360,7 +372,8 @@ static int begin_session(v2r_idw_ctx *ctx, const double *x, const double *y, con
     return V2R_IDW_OK;
 }
 
-// Delivers the next (device, sub-band).  out_base + e*plane_stride + row_off*cols receives exponent e.
+// Delivers the next slice (<= slice_rows rows) of the next (round, device) band.
+// out_base + e*plane_stride + row_off*cols receives exponent e (pack: planes of the slice's own height).
 static int next_band(v2r_idw_ctx *ctx, double *out_base, long long plane_stride, bool pack, long long *o_row0, long long *o_nrows) {
     Session &s = ctx->ses;
     if (!s.active) return set_error(V2R_IDW_ESTATE, "no streaming session is open");
@@ -372,51 +385,63 @@ static int next_band(v2r_idw_ctx *ctx, double *out_base, long long plane_stride,
             *o_nrows = 0;
             return V2R_IDW_OK;
         }
-        if (s.cur_dev == 0 && s.cur_round + 1 < s.rounds) {
+        const bool band_start = s.slice_off == 0;
+        if (band_start && s.cur_dev == 0 && s.cur_round + 1 < s.rounds) {
             int rc = launch_round(ctx, s.cur_round + 1);  // next round computes while this one is copied out
             if (rc) return rc;
         }
         DeviceState &d = ctx->dev[s.cur_dev];
+        DeviceState &d0 = ctx->dev[0];
         const int buf = (int)(s.cur_round & 1);
+        const int g = s.cur_dev;
         long long r0, nr;
         sub_band(s, d, s.cur_round, &r0, &nr);
-        const int g = s.cur_dev;
-        if (++s.cur_dev == G) { s.cur_dev = 0; ++s.cur_round; }
-        if (nr <= 0) continue;
-
-        DeviceState &d0 = ctx->dev[0];
-        const double *src = d.d_band[buf];
-        const size_t cnt = (size_t)nr * (size_t)s.grid.cols * (size_t)E;
-        CUDA_TRY(cudaSetDevice(d.device));
-        CUDA_TRY(cudaStreamWaitEvent(d.copy, d.k_stop[buf], 0));
-        if (g != 0) {  // gather the band to rank 0 over NVLink (north_star), then copy out from there
-            NCCL_TRY(g_nccl.GroupStart());
-            NCCL_TRY(g_nccl.Send(src, cnt, ncclDouble, 0, d.comm, d.copy));
-            NCCL_TRY(g_nccl.Recv(ctx->d_gather, cnt, ncclDouble, g, d0.comm, d0.copy));
-            NCCL_TRY(g_nccl.GroupEnd());
-            src = ctx->d_gather;
-            CUDA_TRY(cudaSetDevice(d0.device));
+        if (nr <= 0) {
+            if (++s.cur_dev == G) { s.cur_dev = 0; ++s.cur_round; }
+            continue;
         }
-        CUDA_TRY(cudaEventRecord(d0.c_start, d0.copy));
         const long long plane_src = nr * s.grid.cols;
-        const long long stride = pack ? plane_src : plane_stride;
-        const long long off = pack ? 0 : (r0 - s.row0) * s.grid.cols;
+        if (band_start) {
+            CUDA_TRY(cudaSetDevice(d.device));
+            CUDA_TRY(cudaStreamWaitEvent(d.copy, d.k_stop[buf], 0));
+            if (g != 0) {  // gather the whole band to rank 0 over NVLink (north_star); slices are copied out from there
+                NCCL_TRY(g_nccl.GroupStart());
+                NCCL_TRY(g_nccl.Send(d.d_band[buf], (size_t)plane_src * E, ncclDouble, 0, d.comm, d.copy));
+                NCCL_TRY(g_nccl.Recv(ctx->d_gather, (size_t)plane_src * E, ncclDouble, g, d0.comm, d0.copy));
+                NCCL_TRY(g_nccl.GroupEnd());
+            } else {
+                CUDA_TRY(cudaStreamSynchronize(d.copy));  // kernel of this band finished
+            }
+            float ms = 0;
+            if (g != 0) {
+                CUDA_TRY(cudaStreamSynchronize(d.copy));
+                CUDA_TRY(cudaSetDevice(d0.device));
+                CUDA_TRY(cudaStreamSynchronize(d0.copy));
+            }
+            if (cudaEventElapsedTime(&ms, d.k_start[buf], d.k_stop[buf]) == cudaSuccess) d.kernel_ms += ms;
+        }
+        const double *src = (g != 0) ? ctx->d_gather : d.d_band[buf];
+        const long long sr0 = r0 + s.slice_off, snr = std::min(s.slice_rows, nr - s.slice_off);
+        CUDA_TRY(cudaSetDevice(d0.device));
+        CUDA_TRY(cudaEventRecord(d0.c_start, d0.copy));
+        const long long plane_dst = snr * s.grid.cols;
+        const long long stride = pack ? plane_dst : plane_stride;
+        const long long off = pack ? 0 : (sr0 - s.row0) * s.grid.cols;
         for (int e = 0; e < E; ++e)
-            CUDA_TRY(cudaMemcpyAsync(out_base + (long long)e * stride + off, src + (long long)e * plane_src,
-                                     (size_t)plane_src * 8, cudaMemcpyDeviceToHost, d0.copy));
+            CUDA_TRY(cudaMemcpyAsync(out_base + (long long)e * stride + off, src + (long long)e * plane_src + s.slice_off * s.grid.cols,
+                                     (size_t)plane_dst * 8, cudaMemcpyDeviceToHost, d0.copy));
         CUDA_TRY(cudaEventRecord(d0.c_stop, d0.copy));
         CUDA_TRY(cudaStreamSynchronize(d0.copy));
-        if (g != 0) {
-            CUDA_TRY(cudaSetDevice(d.device));
-            CUDA_TRY(cudaStreamSynchronize(d.copy));
-        }
         float ms = 0;
         cudaEventElapsedTime(&ms, d0.c_start, d0.c_stop);
         ctx->d2h_ms += ms;
-        cudaEventElapsedTime(&ms, d.k_start[buf], d.k_stop[buf]);
-        d.kernel_ms += ms;
-        *o_row0 = r0;
-        *o_nrows = nr;
+        s.slice_off += snr;
+        if (s.slice_off >= nr) {
+            s.slice_off = 0;
+            if (++s.cur_dev == G) { s.cur_dev = 0; ++s.cur_round; }
+        }
+        *o_row0 = sr0;
+        *o_nrows = snr;
         return V2R_IDW_OK;
     }
 }
