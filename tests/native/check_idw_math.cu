@@ -25,11 +25,17 @@ int main() {
         if (rh > maxh) maxh = rh;
     }
     int bad = 0;
-    bad += !(fast_log2(0.0) == -INFINITY) + !(fast_log2(-0.0) == -INFINITY) + !(fast_log2(INFINITY) == INFINITY) + !std::isnan(fast_log2(NAN));
-    bad += !(fast_log2(1.0) == 0.0) + !(fast_log2(2.0) == 1.0) + !(fast_log2(0.5) == -1.0) + !(fast_log2(1e-320) == -INFINITY);
-    const double ts[] = {0, 1, -1, 1023, 1024, 1100, -1022, -1074, -1075, -3000, 3000, INFINITY, -INFINITY, 2039.5, -2039.5, 2040, -2040, 2047.9};
+    // saturating specials: log2(0) is a huge negative FINITE number, inf / NaN give NaN
+    for (double a0 : {0.0, -0.0, 1e-320}) bad += !(fast_log2(a0) < -1e300 && std::isfinite(fast_log2(a0)));
+    bad += !std::isnan(fast_log2(INFINITY)) + !std::isnan(fast_log2(NAN));
+    bad += !(fast_log2(1.0) == 0.0) + !(fast_log2(2.0) == 1.0) + !(fast_log2(0.5) == -1.0);
+    const double ts[] = {0, -0.0, 1, -1, 1022, 1023, 1023.9, 1024, 1100, -1021, -3000, 3000, 2039.5, -2039.5, 2040, -2040, 2047.9, 1e300, -1e300};
     for (double t : ts) bad += !(fast_exp2(t) == exp2(t));
+    for (double t : {-1022.5, -1040.0, -1074.0, -1075.0}) bad += !(fabs(fast_exp2(t) - exp2(t)) <= 1e-323);   // through the subnormals (+-2 quanta)
     bad += !std::isnan(fast_exp2(NAN));
+    // the compositions the kernel relies on: d2 = 0 with p > 0 -> +inf, p < 0 -> 0, p == 0 -> exactly 1
+    bad += !(fast_exp2(-0.85 * fast_log2(0.0)) == INFINITY) + !(fast_exp2(0.5 * fast_log2(0.0)) == 0.0) + !(fast_exp2(0.0 * fast_log2(0.0)) == 1.0);
+    bad += !(fast_exp2(-0.0 * fast_log2(123.0)) == 1.0) + !std::isnan(fast_exp2(-0.85 * fast_log2(NAN)));
     printf("%.3e %.3e %.3e %d\n", maxl, maxe, maxh, bad);
     return 0;
 }

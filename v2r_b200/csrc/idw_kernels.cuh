@@ -173,13 +173,9 @@ __device__ __forceinline__ void weights(double d2, const KParams &p, double (&h)
         const double L = fast_log2(d2);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const double c = p.cexp[e];
-            // Go: Pow(d, -0) == 1 even at d == 0 (where c*L would be 0*inf).  The zero test is on the integer words
-            // and only replaces the ARGUMENT: exp2(0) is exactly 1, and keeping fast_exp2 unconditional keeps all
-            // cells' chains in one basic block (a branch per cell serialised them: 17 dependent FP64 ops each).
-            double t = c * L;
-            if (((hi_word(c) & 0x7fffffff) | lo_word(c)) == 0) t = 0.0;
-            h[e] = fast_exp2(t);
+            // L is finite (saturating log2), so p == 0 gives c * L == 0 and exp2(0) == 1 exactly: Go's
+            // Pow(d, -0) == 1 even at d == 0 needs no special case; d == 0 with p > 0 gives 2^(+huge) = +inf.
+            h[e] = fast_exp2(p.cexp[e] * L);
         }
     } else {
         double b = base_pow<MODE>(d2);

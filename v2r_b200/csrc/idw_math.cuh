@@ -5,8 +5,9 @@
 // integer instructions on the high/low words (ALU pipe, otherwise idle), and there are no FP64 compares.
 //   fast_log2 : 16 FP64 + 1 MUFU.RCP64H   (FDLIBM e_log.c style: s = f/(2+f), 7-term series in s^2)
 //   fast_exp2 : 17 FP64                   (round-to-int by magic add, exp(x/2) Taylor degree 10, one squaring,
-//                                          two-step 2^n scaling so overflow/underflow saturate correctly)
-// libdevice's log2()/exp2() need roughly twice as many (measured: the kernel was 2.4x slower with them).
+//                                          2^n as two exact power-of-two factors so the result saturates)
+// Both SATURATE instead of producing infinities from finite-range inputs (log2(0) = -2^1000), which removes
+// every special case from the kernel.  With libdevice's log2()/exp2() the kernel was 1.9x slower.
 // Subnormal d2 is flushed to zero like rcp.approx.ftz does in the other classes.
 // __host__ versions exist only so tests/ can compile this header on the CPU and compare with libm.
 #pragma once
@@ -68,9 +69,12 @@ __host__ __device__ __forceinline__ double int2double(int k) {
 #endif
 }
 
-// log2(a) for a >= 0.  a == 0 (or subnormal) -> -inf, +inf -> +inf, NaN -> NaN.
+// log2(a) for a >= 0, SATURATING: a == 0 (or subnormal, flushed like rcp.approx.ftz) -> -2^1000, +inf / NaN -> NaN.
+// The result is therefore always finite or NaN, so c * L is never inf and 0 * L == 0: the caller needs no special
+// case for p == 0 (Go: Pow(d, -0) == 1 even at d == 0) and fast_exp2 needs no inf handling.
+// 16 FP64 + MUFU.RCP64H + I2F; specials cost two integer compares and two selects on the HIGH word only.
 __host__ __device__ __forceinline__ double fast_log2(double a) {
-    int hi = hi_word(a);
+    const int hi = hi_word(a);
     const int lo = lo_word(a);
     // m in [sqrt(1/2), sqrt(2)):  mantissa above 0x6a09e (sqrt2) folds into the lower binade
     int k = (hi >> 20) - 1023;
@@ -94,25 +98,23 @@ __host__ __device__ __forceinline__ double fast_log2(double a) {
     p = fma(p, z, kLg[0]);
     const double q = p * z;                   // log(m) = 2s + s*q
     const double lm = fma(s, q, s + s);
-    double L = fma(lm, kMisc[0], int2double(k));
-    // specials by integer tests only
-    if (hi < 0x00100000) L = make_double((int)0xfff00000, 0);             // zero / subnormal -> -inf
-    if (hi >= 0x7ff00000) L = a;                                          // +inf / NaN pass through
-    return L;
+    const double L = fma(lm, kMisc[0], int2double(k));
+    int lhi = hi_word(L);
+    if (hi < 0x00100000) lhi = (int)0xfe700000;   // zero / subnormal (/ negative): -2^1000-ish, finite
+    if (hi >= 0x7ff00000) lhi = 0x7ff80000;       // +inf / NaN: NaN
+    return make_double(lhi, lo_word(L));
 }
 
-// 2^t for any t (saturates to 0 / +inf, NaN -> NaN).
+// 2^t for finite t (any magnitude) or NaN.  Saturates: t >= 1024 -> +inf, t <= -1075 -> 0.  17 FP64.
 __host__ __device__ __forceinline__ double fast_exp2(double t) {
-    int hi = hi_word(t);
-    const int ahi = hi & 0x7fffffff;
-    // clamp |t| >= 2040 (incl. +-inf) to +-2040: the result is 0 / +inf there anyway, the reduction below
-    // stays exact and both halves of 2^n keep a normal exponent field; NaN is left alone
-    if (ahi >= 0x409fe000 && (ahi < 0x7ff00000 || (ahi == 0x7ff00000 && lo_word(t) == 0)))
-        t = make_double((hi & (int)0x80000000) | 0x409fe000, 0);
-    const double magic = kMisc[1];            // 1.5 * 2^52: adding it rounds t to the nearest integer
-    const double tn = t + magic;
+    const int hi = hi_word(t);
+    // clamp 2040 <= |t| < inf to +-2040 with one unsigned range test (NaN / inf fall outside and pass through)
+    const bool big = (unsigned)((hi & 0x7fffffff) - 0x409fe000) < (unsigned)(0x7ff00000 - 0x409fe000);
+    const double tc = make_double(big ? ((hi & (int)0x80000000) | 0x409fe000) : hi, big ? 0 : lo_word(t));
+    const double magic = kMisc[1];            // 1.5 * 2^52: adding it rounds to the nearest integer
+    const double tn = tc + magic;
     const int n = lo_word(tn);                // integer part (two's complement in the low word)
-    const double f = t - (tn - magic);        // in [-1/2, 1/2]
+    const double f = tc - (tn - magic);       // in [-1/2, 1/2]
     const double x = f * kMisc[2];            // (ln 2)/2 * f : exp(x)^2 = 2^f, |x| <= 0.1733
     double p = kEx[0];                        // Taylor 1/10! .. 1/2!
 #pragma unroll
@@ -120,10 +122,10 @@ __host__ __device__ __forceinline__ double fast_exp2(double t) {
     p = fma(p, x, 1.0);
     p = fma(p, x, 1.0);
     p = p * p;
-    // 2^n in two steps (n in [-2040, 2040]): each factor has a normal exponent field
+    // 2^n in two factors (n in [-2040, 2040], each half keeps a normal exponent field): overflow saturates to
+    // +inf, underflow rounds through the subnormals to 0, NaN stays NaN -- all by the multiplies themselves
     const int n1 = n >> 1, n2 = n - n1;
-    const double s1 = make_double((n1 + 1023) << 20, 0), s2 = make_double((n2 + 1023) << 20, 0);
-    return (p * s1) * s2;
+    return (p * make_double((n1 + 1023) << 20, 0)) * make_double((n2 + 1023) << 20, 0);
 }
 
 }  // namespace v2r
