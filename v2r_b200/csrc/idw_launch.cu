@@ -112,7 +112,7 @@ static const Variant kVariants[] = {
     V2R_TUNE("t384", MODE_RCP, 1, 4, 4, 1, 0, 384, 1), V2R_TUNE("t384", MODE_QRT, 1, 4, 4, 3, 0, 384, 1),
     V2R_TUNE("b2", MODE_RCP, 1, 4, 2, 1, 0, 256, 2), V2R_TUNE("b2", MODE_QRT, 9, 1, 2, 1, 1, 256, 2),
     V2R_TUNE("c1x4", MODE_QRT, 9, 1, 4, 1, 1, 256, 1), V2R_TUNE("c4x4", MODE_QRT, 1, 4, 4, 3, 0, 256, 1),
-    V2R_TUNE("g2x4", MODE_GEN, 1, 2, 4, 0, 0, 256, 2), V2R_TUNE("g4x4", MODE_GEN, 1, 4, 4, 0, 0, 256, 1),
+    V2R_TUNE("g2x2", MODE_GEN, 1, 2, 2, 0, 0, 256, 2), V2R_TUNE("g4x4", MODE_GEN, 1, 4, 4, 0, 0, 256, 1),
     V2R_TUNE("g1x2", MODE_GEN, 1, 1, 2, 0, 0, 256, 2),
     Variant{MODE_RCP, 1, 1, 0, 4, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 4, 4, 1, 0, 256, 1, 1>, "MODE_RCP", true, nullptr},  // p = 2, paired (c2, c4)
     V2R_VARIANT(MODE_RCP, 1, 4, 4, 1, 0, 256, 1),   // p = 2, one reciprocal per pair (V2R_IDW_FP64_PAIRED=0)
@@ -126,7 +126,7 @@ static const Variant kVariants[] = {
     // runtime ladders
     V2R_ROW(MODE_RCP), V2R_ROW(MODE_RSQ), V2R_ROW(MODE_QRT),
     // general exponents: fewer cells per thread (log2/exp2 temporaries)
-    V2R_VARIANT(MODE_GEN, 1, 2, 2, 0, 0, 256, 2), V2R_VARIANT(MODE_GEN, 2, 2, 2, 0, 0, 256, 2),
+    V2R_VARIANT(MODE_GEN, 1, 2, 4, 0, 0, 256, 2), V2R_VARIANT(MODE_GEN, 2, 2, 2, 0, 0, 256, 2),
     V2R_VARIANT(MODE_GEN, 3, 2, 2, 0, 0, 256, 2), V2R_VARIANT(MODE_GEN, 4, 2, 2, 0, 0, 256, 2),
     V2R_VARIANT(MODE_GEN, 5, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE_GEN, 6, 2, 2, 0, 0, 256, 1),
     V2R_VARIANT(MODE_GEN, 7, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE_GEN, 8, 2, 2, 0, 0, 256, 1),
