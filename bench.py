@@ -202,15 +202,12 @@ def ours(args):
     n, E = len(ps), len(exps)
 
     # ---- inputs resident in HBM: rank 0 uploads, NCCL broadcast replicates (outside the timed region)
-    def dev_arr(a, dtype):
-        t = torch.empty(len(a), dtype=dtype, device=dev)
-        if rank == 0:
-            t.copy_(torch.from_numpy(np.ascontiguousarray(a)))
-        if world > 1:
-            dist.broadcast(t, 0)
-        return t
-    dx, dy, dw = dev_arr(ps.x, torch.float64), dev_arr(ps.y, torch.float64), dev_arr(ps.w, torch.float64)
-    dkr, dkc = dev_arr(ps.key_r, torch.int64), dev_arr(ps.key_c, torch.int64)
+    if world > 1:
+        from v2r_b200.distributed import broadcast_points
+        dx, dy, dw, dkr, dkc = broadcast_points(ps if rank == 0 else None, dev)     # ONE packed broadcast
+    else:
+        dx, dy, dw = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (ps.x, ps.y, ps.w))
+        dkr, dkc = (torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev) for a in (ps.key_r, ps.key_c))
     dout = torch.empty((E, nrows, grid.cols), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     exps_c = np.ascontiguousarray(exps, dtype=np.float64)

@@ -99,9 +99,10 @@ static int load_nccl() {
 struct DeviceState {
     int device = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
-    double *d_x = nullptr, *d_y = nullptr, *d_z = nullptr;
+    double *d_pts = nullptr;  // one block: [x | y | z | key_r | key_c], stride pts_stride elements
+    double *d_x = nullptr, *d_y = nullptr, *d_z = nullptr;  // views into d_pts
     long long *d_kr = nullptr, *d_kc = nullptr;
-    size_t pts_cap = 0;  // points
+    size_t pts_cap = 0, pts_stride = 0;  // elements per array
     double *d_band[2] = {nullptr, nullptr};
     size_t band_cap[2] = {0, 0};  // doubles
     cudaEvent_t k_start[2] = {nullptr, nullptr}, k_stop[2] = {nullptr, nullptr};
@@ -142,7 +143,7 @@ namespace v2r {
 static void free_device_state(DeviceState &d) {
     cudaSetDevice(d.device);
     if (d.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d.comm);
-    for (void *p : {(void *)d.d_x, (void *)d.d_y, (void *)d.d_z, (void *)d.d_kr, (void *)d.d_kc, (void *)d.d_band[0], (void *)d.d_band[1]})
+    for (void *p : {(void *)d.d_pts, (void *)d.d_band[0], (void *)d.d_band[1]})
         if (p) cudaFree(p);
     for (cudaEvent_t e : {d.k_start[0], d.k_start[1], d.k_stop[0], d.k_stop[1], d.c_start, d.c_stop, d.up_start, d.up_stop})
         if (e) cudaEventDestroy(e);
@@ -222,26 +223,30 @@ static int ensure(T *&p, size_t &cap, size_t need) {
     return V2R_IDW_OK;
 }
 
+// The five point arrays live in ONE device block [x | y | z | key_r | key_c] with a common stride (all 8-byte
+// elements), so replicating the point set is literally one NCCL broadcast.
 static int ensure_points(DeviceState &d, size_t n) {
-    if (n <= d.pts_cap && d.d_x) return V2R_IDW_OK;
-    CUDA_TRY(cudaSetDevice(d.device));
-    for (void *p : {(void *)d.d_x, (void *)d.d_y, (void *)d.d_z, (void *)d.d_kr, (void *)d.d_kc})
-        if (p) cudaFree(p);
-    d.d_x = d.d_y = d.d_z = nullptr;
-    d.d_kr = d.d_kc = nullptr;
-    d.pts_cap = 0;
-    size_t cap = ((n + (n >> 3) + 1023) / 1024) * 1024;
-    CUDA_TRY(cudaMalloc((void **)&d.d_x, cap * 8));
-    CUDA_TRY(cudaMalloc((void **)&d.d_y, cap * 8));
-    CUDA_TRY(cudaMalloc((void **)&d.d_z, cap * 8));
-    CUDA_TRY(cudaMalloc((void **)&d.d_kr, cap * 8));
-    CUDA_TRY(cudaMalloc((void **)&d.d_kc, cap * 8));
-    d.pts_cap = cap;
+    const size_t stride = ((std::max<size_t>(n, 1) + 1) / 2) * 2;  // even: every array stays 16-byte aligned (TMA)
+    if (stride > d.pts_cap || !d.d_pts) {
+        CUDA_TRY(cudaSetDevice(d.device));
+        if (d.d_pts) cudaFree(d.d_pts);
+        d.d_pts = nullptr;
+        d.pts_cap = 0;
+        const size_t cap = ((stride + (stride >> 3) + 1023) / 1024) * 1024;
+        CUDA_TRY(cudaMalloc((void **)&d.d_pts, cap * 5 * 8));
+        d.pts_cap = cap;
+    }
+    d.pts_stride = stride;
+    d.d_x = d.d_pts;
+    d.d_y = d.d_pts + stride;
+    d.d_z = d.d_pts + 2 * stride;
+    d.d_kr = reinterpret_cast<long long *>(d.d_pts + 3 * stride);
+    d.d_kc = reinterpret_cast<long long *>(d.d_pts + 4 * stride);
     return V2R_IDW_OK;
 }
 
-// Upload points to device 0 and replicate them to every other device with ONE grouped NCCL
-// broadcast per array over NVLink (north_star: "the point set is replicated with one NCCL broadcast").
+// Upload the points to device 0 and replicate them to every other device with ONE NCCL broadcast over NVLink
+// (north_star: "the point set is replicated with one NCCL broadcast"): 5 * stride * 8 bytes, c4: 39 MB.
 static int upload_points(v2r_idw_ctx *ctx, const double *x, const double *y, const double *z, const int64_t *kr,
                          const int64_t *kc, long long n) {
     for (auto &d : ctx->dev) {
@@ -259,17 +264,10 @@ static int upload_points(v2r_idw_ctx *ctx, const double *x, const double *y, con
         CUDA_TRY(cudaMemcpyAsync(d0.d_kc, kc, n * 8, cudaMemcpyHostToDevice, d0.compute));
     }
     if (ctx->dev.size() > 1 && n > 0) {
-        auto arrays = [](DeviceState &d) { return std::array<void *, 5>{d.d_x, d.d_y, d.d_z, d.d_kr, d.d_kc}; };
-        const std::array<void *, 5> src = arrays(d0);
-        for (int a = 0; a < 5; ++a) {  // one grouped broadcast per array: x, y, z (float64), key_r, key_c (int64)
-            NCCL_TRY(g_nccl.GroupStart());
-            for (auto &d : ctx->dev) {
-                void *dst = arrays(d)[a];
-                // the root sends its own array; the other ranks pass their receive buffer for both arguments
-                NCCL_TRY(g_nccl.Broadcast(&d == &d0 ? src[a] : dst, dst, (size_t)n, a < 3 ? ncclDouble : ncclInt64, 0, d.comm, d.compute));
-            }
-            NCCL_TRY(g_nccl.GroupEnd());
-        }
+        NCCL_TRY(g_nccl.GroupStart());  // one collective; the group only spans this process's communicators
+        for (auto &d : ctx->dev)
+            NCCL_TRY(g_nccl.Broadcast(d.d_pts, d.d_pts, 5 * d.pts_stride, ncclDouble, 0, d.comm, d.compute));
+        NCCL_TRY(g_nccl.GroupEnd());
     }
     CUDA_TRY(cudaSetDevice(d0.device));
     CUDA_TRY(cudaEventRecord(d0.up_stop, d0.compute));

@@ -30,23 +30,25 @@ def shard_rows(rows: int, world: int, rank: int, align: int = 32):
 
 
 def broadcast_points(ps: PointSet | None, device, group=None):
-    """Rank 0 passes the PointSet, the others None.  Returns five device tensors (x, y, w, key_r, key_c).
-    One broadcast of the count, then one per array (3*N*8 + 2*N*8 bytes over NVLink)."""
+    """Rank 0 passes the PointSet, the others None.  Returns five device tensors (x, y, w, key_r, key_c), all
+    views of ONE packed [5, stride] float64 block (the int64 keys travel as bit patterns), so the whole point set
+    is replicated by a single broadcast (5*N*8 bytes over NVLink) after a one-element broadcast of the count."""
     import torch
     import torch.distributed as dist
     rank = dist.get_rank(group)
     n = torch.tensor([len(ps) if rank == 0 else 0], dtype=torch.int64, device=device)
     dist.broadcast(n, 0, group=group)
     n = int(n.item())
-    out = []
-    for name, dt, npdt in (("x", torch.float64, np.float64), ("y", torch.float64, np.float64), ("w", torch.float64, np.float64),
-                           ("key_r", torch.int64, np.int64), ("key_c", torch.int64, np.int64)):
-        t = torch.empty(n, dtype=dt, device=device)
-        if rank == 0:
-            t.copy_(torch.from_numpy(np.ascontiguousarray(getattr(ps, name), dtype=npdt)))
-        dist.broadcast(t, 0, group=group)
-        out.append(t)
-    return out
+    stride = (max(n, 1) + 1) // 2 * 2          # even: every row stays 16-byte aligned for the TMA tile loads
+    block = torch.empty((5, stride), dtype=torch.float64, device=device)
+    if rank == 0:
+        host = np.zeros((5, stride), dtype=np.float64)
+        host[0, :n], host[1, :n], host[2, :n] = ps.x, ps.y, ps.w
+        host[3, :n] = np.ascontiguousarray(ps.key_r, dtype=np.int64).view(np.float64)
+        host[4, :n] = np.ascontiguousarray(ps.key_c, dtype=np.int64).view(np.float64)
+        block.copy_(torch.from_numpy(host))
+    dist.broadcast(block, 0, group=group)
+    return [block[0, :n], block[1, :n], block[2, :n], block[3, :n].view(torch.int64), block[4, :n].view(torch.int64)]
 
 
 def cuda_band(dev_points, grid, row0, nrows, exps, precision, device_index):
