@@ -114,6 +114,9 @@ static const Variant kVariants[] = {
     V2R_TUNE("c1x4", MODE_QRT, 9, 1, 4, 1, 1, 256, 1), V2R_TUNE("c4x4", MODE_QRT, 1, 4, 4, 3, 0, 256, 1),
     V2R_TUNE("g2x2", MODE_GEN, 1, 2, 2, 0, 0, 256, 2), V2R_TUNE("g4x4", MODE_GEN, 1, 4, 4, 0, 0, 256, 1),
     V2R_TUNE("g1x2", MODE_GEN, 1, 1, 2, 0, 0, 256, 2),
+    Variant{MODE_RCP, 1, 1, 0, 6, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 6, 4, 1, 0, 256, 1, 1>, "MODE_RCP", true, "c6x4"},
+    Variant{MODE_RCP, 1, 1, 0, 4, 6, 256, idw_fp64_kernel<MODE_RCP, 1, 4, 6, 1, 0, 256, 1, 1>, "MODE_RCP", true, "c4x6"},
+    Variant{MODE_RCP, 1, 1, 0, 5, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 5, 4, 1, 0, 256, 1, 1>, "MODE_RCP", true, "c5x4"},
     Variant{MODE_RCP, 1, 1, 0, 4, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 4, 4, 1, 0, 256, 1, 1>, "MODE_RCP", true, nullptr},  // p = 2, paired (c2, c4)
     V2R_VARIANT(MODE_RCP, 1, 4, 4, 1, 0, 256, 1),   // p = 2, one reciprocal per pair (V2R_IDW_FP64_PAIRED=0)
     // rsqrt / root4 bases have longer dependent chains: 2x4 cells at two CTAs per SM measured +8 % over 4x4 at one
