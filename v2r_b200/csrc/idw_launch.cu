@@ -238,7 +238,7 @@ int launch_rows_fp64(cudaStream_t stream, const double *d_x, const double *d_y, 
         const long long tile_r = (long long)(v->threads / 32) * v->cr, tile_c = 32LL * v->cc;
         const long long gx = (g.cols + tile_c - 1) / tile_c, gy = (nrows + tile_r - 1) / tile_r;
         if (gx > 2147483647LL || gy > 65535LL)
-            return set_error(V2R_IDW_EINVAL, "band of %lld rows x %lld cols exceeds one launch; use smaller bands", nrows, g.cols);
+            return set_error(V2R_IDW_EINVAL, "band of %lld rows x %lld cols exceeds one launch; use smaller bands", nrows, (long long)g.cols);
         v->fn<<<dim3((unsigned)gx, (unsigned)gy), v->threads, 0, stream>>>(kp);
         g_launches++;
         cudaError_t ce = cudaGetLastError();
@@ -416,7 +416,7 @@ extern "C" int v2r_idw_measure_peaks(int device, double ms, double *dfma, double
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (ms <= 0) ms = 50;
-    double v;
+    double v = 0;
     int rc;
     if (dfma) { if ((rc = run_peak<0>(ms, sms, &v))) return rc; *dfma = v; }
     if (mufu64) { if ((rc = run_peak<1>(ms, sms, &v))) return rc; *mufu64 = v; }

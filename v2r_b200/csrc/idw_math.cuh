@@ -117,8 +117,14 @@ __host__ __device__ __forceinline__ double fast_exp2(double t) {
     const double f = tc - (tn - magic);       // in [-1/2, 1/2]
     const double x = f * kMisc[2];            // (ln 2)/2 * f : exp(x)^2 = 2^f, |x| <= 0.1733
     double p = kEx[0];                        // Taylor 1/10! .. 1/2!
-#pragma unroll
-    for (int i = 1; i < 9; ++i) p = fma(p, x, kEx[i]);
+    p = fma(p, x, kEx[1]);
+    p = fma(p, x, kEx[2]);
+    p = fma(p, x, kEx[3]);
+    p = fma(p, x, kEx[4]);
+    p = fma(p, x, kEx[5]);
+    p = fma(p, x, kEx[6]);
+    p = fma(p, x, kEx[7]);
+    p = fma(p, x, kEx[8]);
     p = fma(p, x, 1.0);
     p = fma(p, x, 1.0);
     p = p * p;
