@@ -291,6 +291,10 @@ def ours(args):
             except Exception:
                 traffic = None
         peaks = {"dfma": dfma.value, "mufu_rcp64h": m64.value, "mufu_rcp_f32": m32.value, "ffma": ffma.value}
+        for key, which in (("dfma_3src", 4), ("dadd", 5)):   # the operand forms the kernels actually issue
+            v = C.c_double()
+            _lib.check(L.v2r_idw_measure_peak(local, 60.0, which, C.byref(v)))
+            peaks[key] = v.value
         if prec == _lib.FP64:
             # FP64-pipe roofline: algorithmic slots per pair x 2 flop, against the DFMA issue rate
             achieved_tflops = per_gpu_pairs_s * 2 * A / 1e12
@@ -302,6 +306,7 @@ def ours(args):
                 "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP64_TFLOPS,
                 "algorithmic_fp64_slots_per_pair": A, "issued_fp64_slots_per_pair_model": ops.value,
                 "fp64_pipe_busy_model": per_gpu_pairs_s * ops.value / (dfma.value * 1e9) if dfma.value else None,
+                "frac_of_3src_dfma_rate_at_issued_slots": per_gpu_pairs_s * ops.value / (peaks["dfma_3src"] * 1e9) if peaks.get("dfma_3src") else None,
                 "kernel": buf.value.decode(), "ms_per_launch": ms_total / args.steps, "measured_peaks_ginst_s": peaks,
             }
         else:

@@ -157,6 +157,16 @@ int v2r_idw_describe(const double *exps, int n_exps, int precision, char *buf, s
 int v2r_idw_measure_peaks(int device, double ms, double *dfma_ginst_s, double *mufu64_ginst_s,
                           double *mufu32_ginst_s, double *ffma_ginst_s);
 
+/* One microbenchmark at a time.  DFMA_3SRC issues DFMAs with three distinct register-pair sources -- the form
+ * the IDW kernels execute -- as opposed to DFMA's one register source + two constants. */
+#define V2R_IDW_PEAK_DFMA         0
+#define V2R_IDW_PEAK_MUFU_RCP64H  1
+#define V2R_IDW_PEAK_MUFU_RCP_F32 2
+#define V2R_IDW_PEAK_FFMA         3
+#define V2R_IDW_PEAK_DFMA_3SRC    4
+#define V2R_IDW_PEAK_DADD         5
+int v2r_idw_measure_peak(int device, double ms, int which, double *ginst_s);
+
 #ifdef __cplusplus
 }
 #endif

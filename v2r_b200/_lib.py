@@ -56,6 +56,7 @@ SIGNATURES = {
     "v2r_idw_launch_count": (C.c_int64, []),
     "v2r_idw_describe": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p, C.c_size_t, _D]),
     "v2r_idw_measure_peaks": (C.c_int, [C.c_int, C.c_double, _D, _D, _D, _D]),
+    "v2r_idw_measure_peak": (C.c_int, [C.c_int, C.c_double, C.c_int, _D]),
 }
 
 _lib = None

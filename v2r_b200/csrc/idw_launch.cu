@@ -361,6 +361,33 @@ __global__ void __launch_bounds__(256) peak_kernel(double *out, int iters) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) t += a[j];
         if (t == 12345.678f) out[0] = t;
+    } else if constexpr (WHICH == 4) {  // DFMA with three distinct register-pair sources (what the IDW kernels issue)
+        double a[8], b[8], c[8];
+#pragma unroll
+        const double rnd = 1e-12 * (double)((clock64() + threadIdx.x) & 1023);  // unknown at compile time: operands must live in registers
+        for (int j = 0; j < 8; ++j) { a[j] = s + j; b[j] = 0.999999 + rnd * (j + 1); c[j] = 1.000001 - rnd * (2 * j + 1); }
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = fma(b[j], c[(j + 1) & 7], a[j]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = fma(a[j], c[j], b[(j + 3) & 7]);
+        }
+        double t = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += a[j] + b[j];
+        if (t == 12345.678) out[0] = t;
+    } else if constexpr (WHICH == 5) {  // DADD, two register sources
+        double a[8], b[8];
+#pragma unroll
+        const double rnd = 1e-12 * (double)((clock64() + threadIdx.x) & 1023);
+        for (int j = 0; j < 8; ++j) { a[j] = s + j; b[j] = rnd * (j + 1); }
+        for (int i = 0; i < iters; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = a[j] + b[(j + (i & 1)) & 7];
+        double t = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += a[j];
+        if (t == 12345.678) out[0] = t;
     } else {  // FFMA
         float a[8];
 #pragma unroll
@@ -397,7 +424,7 @@ static int run_peak(double ms_target, int sms, double *ginst) {
             return set_error(V2R_IDW_ECUDA, "peak kernel: %s", cudaGetErrorString(cudaGetLastError()));
         }
         cudaEventElapsedTime(&ms, a, b);
-        double rate = (double)blocks * 256 * iters * 8 / (ms * 1e-3) / 1e9;
+        double rate = (double)blocks * 256 * iters * (WHICH == 4 ? 16 : 8) / (ms * 1e-3) / 1e9;
         if (rep > 0 && rate > best) best = rate;
         if (ms < ms_target) iters = (int)(iters * (ms_target / (ms > 0.01f ? ms : 0.01f)));
         if (iters > 4000000) iters = 4000000;
@@ -423,6 +450,24 @@ extern "C" int v2r_idw_measure_peaks(int device, double ms, double *dfma, double
     if (mufu32) { if ((rc = run_peak<2>(ms, sms, &v))) return rc; *mufu32 = v; }
     if (ffma) { if ((rc = run_peak<3>(ms, sms, &v))) return rc; *ffma = v; }
     return V2R_IDW_OK;
+}
+
+extern "C" int v2r_idw_measure_peak(int device, double ms, int which, double *ginst_s) {
+    if (!ginst_s) return set_error(V2R_IDW_EINVAL, "ginst_s is NULL");
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(ce));
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (ms <= 0) ms = 50;
+    switch (which) {
+        case V2R_IDW_PEAK_DFMA: return run_peak<0>(ms, sms, ginst_s);
+        case V2R_IDW_PEAK_MUFU_RCP64H: return run_peak<1>(ms, sms, ginst_s);
+        case V2R_IDW_PEAK_MUFU_RCP_F32: return run_peak<2>(ms, sms, ginst_s);
+        case V2R_IDW_PEAK_FFMA: return run_peak<3>(ms, sms, ginst_s);
+        case V2R_IDW_PEAK_DFMA_3SRC: return run_peak<4>(ms, sms, ginst_s);
+        case V2R_IDW_PEAK_DADD: return run_peak<5>(ms, sms, ginst_s);
+        default: return set_error(V2R_IDW_EINVAL, "unknown microbenchmark %d", which);
+    }
 }
 
 extern "C" int64_t v2r_idw_launch_count(void) { return launch_count(); }
