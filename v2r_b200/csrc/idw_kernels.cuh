@@ -46,7 +46,7 @@ struct KParams {
     double *out;              // E planes of nrows*cols
     long long plane;          // nrows * cols
     int k0, dk;               // integer power ladder: h_e = b^(k0 + e*dk) (runtime variant)
-    double cexp[kMaxE];       // MODE_GEN: c_e = -p_e/2 (0 => h = 1)
+    double cexp[kMaxE];       // MODE_GEN: 32 * (-p_e/2): the exponent multiplier, pre-scaled for tab_exp2_32
 };
 
 // ---------------------------------------------------------------------------- PTX helpers
@@ -167,15 +167,21 @@ __device__ __forceinline__ void static_powers(double b, double (&h)[E]) {
 }
 
 // h[e] = d2^(-p_e/2) for all exponents of the pass.
+// Shared-memory tables of the general class (2 KB + 256 B), built once per CTA.
+struct GenTables {
+    LogEntry lg[kLogTab];
+    double ex[kExpTab];
+};
+
 template <int MODE, int E, int K0, int DK>
-__device__ __forceinline__ void weights(double d2, const KParams &p, double (&h)[E]) {
+__device__ __forceinline__ void weights(double d2, const KParams &p, const GenTables *gt, double (&h)[E]) {
     if constexpr (MODE == MODE_GEN) {
-        const double L = fast_log2(d2);
+        const double L = tab_log2(d2, gt->lg);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            // L is finite (saturating log2), so p == 0 gives c * L == 0 and exp2(0) == 1 exactly: Go's
-            // Pow(d, -0) == 1 even at d == 0 needs no special case; d == 0 with p > 0 gives 2^(+huge) = +inf.
-            h[e] = fast_exp2(p.cexp[e] * L);
+            // cexp holds 32 * (-p/2).  L is finite (saturating log2), so p == 0 gives 0 * L == 0 and exp2(0) == 1
+            // exactly: Go's Pow(d, -0) == 1 even at d == 0 needs no special case; d == 0 with p > 0 -> +inf.
+            h[e] = tab_exp2_32(p.cexp[e] * L, gt->ex);
         }
     } else {
         double b = base_pow<MODE>(d2);
@@ -206,6 +212,13 @@ __global__ void __launch_bounds__(THREADS, MINB) idw_fp64_kernel(const __grid_co
     constexpr int S = kStages;
     __shared__ __align__(128) double sm[S][3][T];
     __shared__ __align__(8) uint64_t full[S];
+    const GenTables *gt = nullptr;
+    if constexpr (MODE == MODE_GEN) {  // visible to all threads after the __syncthreads that follows the mbarrier init
+        __shared__ __align__(16) GenTables gen_tables;
+        for (int i = threadIdx.x; i < kLogTab; i += THREADS) build_log_entry(i, gen_tables.lg[i]);
+        for (int j = threadIdx.x; j < kExpTab; j += THREADS) gen_tables.ex[j] = build_exp_entry(j);
+        gt = &gen_tables;
+    }
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -312,7 +325,7 @@ __global__ void __launch_bounds__(THREADS, MINB) idw_fp64_kernel(const __grid_co
                 for (int b = 0; b < CC; ++b) {
                     const double d2 = __dadd_rn(dx2[b], dy2[a]);
                     double h[E];
-                    weights<MODE, E, K0, DK>(d2, p, h);
+                    weights<MODE, E, K0, DK>(d2, p, gt, h);
 #pragma unroll
                     for (int e = 0; e < E; ++e) {
                         num[e][a][b] = fma(w, h[e], num[e][a][b]);

@@ -175,7 +175,7 @@ static double model_ops(const Pass &ps, const Variant &v) {
         return hi + m - 1;
     };
     if (ps.mode == MODE_GEN) {
-        ops += 16.0 + 18.0 * E;  // fast_log2 once (16), c*L + fast_exp2 per exponent (1 + 17)
+        ops += 8.0 + 12.0 * E;  // tab_log2 once (8), c*L + tab_exp2_32 per exponent (1 + 11)
     } else {
         ops += ps.mode == MODE_RCP ? 3 : (ps.mode == MODE_RSQ ? 5 : 7);
         if (v.paired) ops -= 0.5;  // 11 instead of 12 instructions per two pairs
@@ -234,7 +234,7 @@ int launch_rows_fp64(cudaStream_t stream, const double *d_x, const double *d_y, 
         kp.plane = plane;
         kp.k0 = ps.k0 > 0 ? ps.k0 : 1;
         kp.dk = ps.dk > 0 ? ps.dk : 1;
-        for (int i = 0; i < ps.count; ++i) kp.cexp[i] = ps.cexp[i];
+        for (int i = 0; i < ps.count; ++i) kp.cexp[i] = 32.0 * ps.cexp[i];  // exact scaling by a power of two
         const long long tile_r = (long long)(v->threads / 32) * v->cr, tile_c = 32LL * v->cc;
         const long long gx = (g.cols + tile_c - 1) / tile_c, gy = (nrows + tile_r - 1) / tile_r;
         if (gx > 2147483647LL || gy > 65535LL)

@@ -1,35 +1,41 @@
 // idw_math.cuh -- software log2 / exp2 for the `general` exponent class (h = exp2(c * log2 d2)).
 //
 // The FP64 pipe is the bottleneck of every IDW kernel, so these are written for the fewest FP64-pipe
-// instructions that still give ~2 ulp: all range reduction, special-case handling and scaling is done with
-// integer instructions on the high/low words (ALU pipe, otherwise idle), and there are no FP64 compares.
-//   fast_log2 : 16 FP64 + 1 MUFU.RCP64H   (FDLIBM e_log.c style: s = f/(2+f), 7-term series in s^2)
-//   fast_exp2 : 17 FP64                   (round-to-int by magic add, exp(x/2) Taylor degree 10, one squaring,
-//                                          2^n as two exact power-of-two factors so the result saturates)
-// Both SATURATE instead of producing infinities from finite-range inputs (log2(0) = -2^1000), which removes
-// every special case from the kernel.  With libdevice's log2()/exp2() the kernel was 1.9x slower.
-// Subnormal d2 is flushed to zero like rcp.approx.ftz does in the other classes.
+// instructions that still give ~1e-15: table-driven argument reduction (tables live in shared memory, built once
+// per CTA), short series with coefficients in the constant bank, and all range reduction, special-case handling
+// and 2^n scaling on the integer pipe (no FP64 compares, no branches).
+//   tab_log2    : 8 FP64 + I2F + one 16-byte table load  (128 entries {1/c_i, -log2(1/c_i)}, degree-6 series)
+//   tab_exp2_32 : 11 FP64 + one 8-byte table load        (32 entries 2^(j/32), degree-6 series)
+// Both SATURATE instead of producing infinities from finite-range inputs (log2(0) = -2^1000-ish), which removes
+// every special case from the kernel: c*L is never inf, and 0*L == 0 gives exp2(0) == 1 exactly (Go: Pow(d,-0) == 1
+// even at d == 0).  Subnormal d2 is flushed to zero like rcp.approx.ftz does in the other classes.
+// History (c2 band, p = 1.7, G evals/s): libdevice log2()/exp2() 218; table-free FDLIBM-style versions (16 + 17
+// FP64 instructions) 302, then 367 once their coefficients sat in the constant bank and the per-cell branches
+// were gone; the table-driven versions here need 19 instead of 33.
 // __host__ versions exist only so tests/ can compile this header on the CPU and compare with libm.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 
 namespace v2r {
 
-// Polynomial coefficients live in the constant bank on the device: an FP64 instruction can take a c[bank][off]
-// operand directly, whereas 64-bit literals were being rebuilt with two UMOVs per use (71 per loop iteration,
-// which made the general-class kernel issue-bound).
 #ifdef __CUDA_ARCH__
 #define V2R_COEF __constant__
 #else
 #define V2R_COEF static const
 #endif
-V2R_COEF double kLg[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
-                          1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01};  // Lg1..Lg7, FDLIBM e_log.c
-V2R_COEF double kEx[9] = {2.7557319223985893e-07, 2.7557319223985888e-06, 2.4801587301587302e-05, 1.9841269841269841e-04,
-                          1.3888888888888889e-03, 8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};  // 1/10! .. 1/2!
-V2R_COEF double kMisc[3] = {1.4426950408889634074, 6755399441055744.0, 0.34657359027997265471};  // log2(e), 1.5*2^52, ln(2)/2
+// log2(1+r) = r * (kLg[0] + kLg[1] r + ... + kLg[5] r^5),  kLg[k] = log2(e) * (-1)^k / (k+1);  |r| <= 2^-8
+V2R_COEF double kLg[6] = {1.4426950408889634074, -0.72134752044448170368, 0.48089834696298780245,
+                          -0.36067376022224085184, 0.28853900817779268147, -0.24044917348149390123};
+// 2^(g/32) = 1 + g * (kEx[0] + kEx[1] g + ... + kEx[5] g^5),  kEx[k] = (ln2/32)^(k+1) / (k+1)!;  |g| <= 1/2
+V2R_COEF double kEx[6] = {0.021660849392498290919, 0.00023459619820224678939, 1.6938509724371820054e-6,
+                          9.1725627018246432895e-9, 3.9737099845494161318e-11, 1.4345655584131935569e-13};
+V2R_COEF double kMagic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
+
+struct LogEntry { double inv_c, log2_c; };  // 1/c_i rounded to double, and -log2 of that rounded value
+constexpr int kLogTab = 128, kExpTab = 32;
 
 __host__ __device__ __forceinline__ int hi_word(double a) {
 #ifdef __CUDA_ARCH__
@@ -52,15 +58,6 @@ __host__ __device__ __forceinline__ double make_double(int hi, int lo) {
     uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double a; memcpy(&a, &u, 8); return a;
 #endif
 }
-__host__ __device__ __forceinline__ double rcp20(double a) {  // ~2^-20 reciprocal seed
-#ifdef __CUDA_ARCH__
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-    return r;
-#else
-    return make_double(hi_word(1.0 / make_double(hi_word(a), 0)), 0);
-#endif
-}
 __host__ __device__ __forceinline__ double int2double(int k) {
 #ifdef __CUDA_ARCH__
     return __int2double_rn(k);
@@ -69,69 +66,60 @@ __host__ __device__ __forceinline__ double int2double(int k) {
 #endif
 }
 
-// log2(a) for a >= 0, SATURATING: a == 0 (or subnormal, flushed like rcp.approx.ftz) -> -2^1000, +inf / NaN -> NaN.
-// The result is therefore always finite or NaN, so c * L is never inf and 0 * L == 0: the caller needs no special
-// case for p == 0 (Go: Pow(d, -0) == 1 even at d == 0) and fast_exp2 needs no inf handling.
-// 16 FP64 + MUFU.RCP64H + I2F; specials cost two integer compares and two selects on the HIGH word only.
-__host__ __device__ __forceinline__ double fast_log2(double a) {
+// Entry i of the tables (the CTA builds them once, one entry per thread, before the point loop).
+// c_i is the midpoint of the i-th 1/128 slice of [1,2); log2_c is taken from the ROUNDED reciprocal, so
+// log2(m) = log2_c + log2(m * inv_c) holds exactly for the numbers actually used.
+__host__ __device__ inline void build_log_entry(int i, LogEntry &e) {
+    const double c = 1.0 + (i + 0.5) / kLogTab;
+    e.inv_c = 1.0 / c;
+    e.log2_c = -log2(e.inv_c);
+}
+__host__ __device__ inline double build_exp_entry(int j) { return exp2((double)j / kExpTab); }
+
+// log2(a) for a >= 0, SATURATING: a == 0 (or subnormal / negative) -> about -2^1000 (finite), +inf / NaN -> NaN.
+__host__ __device__ __forceinline__ double tab_log2(double a, const LogEntry *tab) {
     const int hi = hi_word(a);
-    const int lo = lo_word(a);
-    // m in [sqrt(1/2), sqrt(2)):  mantissa above 0x6a09e (sqrt2) folds into the lower binade
-    int k = (hi >> 20) - 1023;
-    int mhi = (hi & 0x000fffff) | 0x3ff00000;
-    if (mhi >= 0x3ff6a09f) { mhi -= 0x00100000; k += 1; }
-    const double m = make_double(mhi, lo);
-    const double f = m - 1.0;                 // exact
-    const double t = 2.0 + f;
-    double r = rcp20(t);                      // 1/(2+f): seed + cubic step
-    const double e = fma(-t, r, 1.0);
-    const double e2 = fma(e, e, e);
-    r = fma(r, e2, r);
-    const double s = f * r;
-    const double z = s * s;
-    double p = kLg[6];                        // Lg7 .. Lg1
-    p = fma(p, z, kLg[5]);
-    p = fma(p, z, kLg[4]);
-    p = fma(p, z, kLg[3]);
-    p = fma(p, z, kLg[2]);
-    p = fma(p, z, kLg[1]);
-    p = fma(p, z, kLg[0]);
-    const double q = p * z;                   // log(m) = 2s + s*q
-    const double lm = fma(s, q, s + s);
-    const double L = fma(lm, kMisc[0], int2double(k));
+    const int k = (hi >> 20) - 1023;
+    const LogEntry t = tab[(hi >> 13) & (kLogTab - 1)];
+    const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(a));  // [1, 2)
+    const double r = fma(m, t.inv_c, -1.0);                                    // |r| <= 2^-8
+    double q = kLg[5];
+    q = fma(q, r, kLg[4]);
+    q = fma(q, r, kLg[3]);
+    q = fma(q, r, kLg[2]);
+    q = fma(q, r, kLg[1]);
+    q = fma(q, r, kLg[0]);
+    const double L = fma(q, r, int2double(k) + t.log2_c);
     int lhi = hi_word(L);
-    if (hi < 0x00100000) lhi = (int)0xfe700000;   // zero / subnormal (/ negative): -2^1000-ish, finite
+    if (hi < 0x00100000) lhi = (int)0xfe700000;   // zero / subnormal / negative: huge negative, finite
     if (hi >= 0x7ff00000) lhi = 0x7ff80000;       // +inf / NaN: NaN
     return make_double(lhi, lo_word(L));
 }
 
-// 2^t for finite t (any magnitude) or NaN.  Saturates: t >= 1024 -> +inf, t <= -1075 -> 0.  17 FP64.
-__host__ __device__ __forceinline__ double fast_exp2(double t) {
-    const int hi = hi_word(t);
-    // clamp 2040 <= |t| < inf to +-2040 with one unsigned range test (NaN / inf fall outside and pass through)
-    const bool big = (unsigned)((hi & 0x7fffffff) - 0x409fe000) < (unsigned)(0x7ff00000 - 0x409fe000);
-    const double tc = make_double(big ? ((hi & (int)0x80000000) | 0x409fe000) : hi, big ? 0 : lo_word(t));
-    const double magic = kMisc[1];            // 1.5 * 2^52: adding it rounds to the nearest integer
-    const double tn = tc + magic;
-    const int n = lo_word(tn);                // integer part (two's complement in the low word)
-    const double f = tc - (tn - magic);       // in [-1/2, 1/2]
-    const double x = f * kMisc[2];            // (ln 2)/2 * f : exp(x)^2 = 2^f, |x| <= 0.1733
-    double p = kEx[0];                        // Taylor 1/10! .. 1/2!
-    p = fma(p, x, kEx[1]);
-    p = fma(p, x, kEx[2]);
-    p = fma(p, x, kEx[3]);
-    p = fma(p, x, kEx[4]);
-    p = fma(p, x, kEx[5]);
-    p = fma(p, x, kEx[6]);
-    p = fma(p, x, kEx[7]);
-    p = fma(p, x, kEx[8]);
-    p = fma(p, x, 1.0);
-    p = fma(p, x, 1.0);
-    p = p * p;
-    // 2^n in two factors (n in [-2040, 2040], each half keeps a normal exponent field): overflow saturates to
-    // +inf, underflow rounds through the subnormals to 0, NaN stays NaN -- all by the multiplies themselves
+// 2^(T/32) for finite T (any magnitude) or NaN; the caller folds the factor 32 into its multiplier.
+// Saturates: T/32 >= 1024 -> +inf, T/32 <= -1075 -> 0.
+__host__ __device__ __forceinline__ double tab_exp2_32(double T, const double *tab) {
+    const int hi = hi_word(T);
+    // clamp 65280 <= |T| < inf (i.e. |T/32| >= 2040) to +-65280 with one unsigned range test; NaN passes through
+    const bool big = (unsigned)((hi & 0x7fffffff) - 0x40efe000) < (unsigned)(0x7ff00000 - 0x40efe000);
+    const double Tc = make_double(big ? ((hi & (int)0x80000000) | 0x40efe000) : hi, big ? 0 : lo_word(T));
+    const double Tn = Tc + kMagic;
+    const int N = lo_word(Tn);                // nearest integer to T (two's complement in the low word)
+    const double g = Tc - (Tn - kMagic);      // in [-1/2, 1/2], exact
+    double p = kEx[5];
+    p = fma(p, g, kEx[4]);
+    p = fma(p, g, kEx[3]);
+    p = fma(p, g, kEx[2]);
+    p = fma(p, g, kEx[1]);
+    p = fma(p, g, kEx[0]);
+    p = fma(p, g, 1.0);                       // 2^(g/32)
+    const double e = tab[N & (kExpTab - 1)];  // 2^(j/32) in [1, 2)
+    const int n = N >> 5;                     // floor(N / 32), |n| <= 2040
     const int n1 = n >> 1, n2 = n - n1;
-    return (p * make_double((n1 + 1023) << 20, 0)) * make_double((n2 + 1023) << 20, 0);
+    // 2^n in two factors, so overflow saturates to +inf and underflow rounds through the subnormals to 0 by the
+    // multiplies themselves; the first factor rides on the table value's exponent field (an integer add)
+    const double s1 = make_double(hi_word(e) + (n1 << 20), lo_word(e));
+    return (p * s1) * make_double((n2 + 1023) << 20, 0);
 }
 
 }  // namespace v2r
