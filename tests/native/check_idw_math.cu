@@ -43,6 +43,17 @@ int main() {
     // the compositions the kernel relies on: d2 = 0 with p > 0 -> +inf, p < 0 -> 0, p == 0 -> exactly 1
     bad += !(fexp2(-0.85 * flog2(0.0)) == INFINITY) + !(fexp2(0.5 * flog2(0.0)) == 0.0) + !(fexp2(0.0 * flog2(0.0)) == 1.0);
     bad += !(fexp2(-0.0 * flog2(123.0)) == 1.0) + !std::isnan(fexp2(-0.85 * flog2(NAN)));
+    // the (0 < p <= 3.75) specialisation: zero / subnormal / inf / NaN are poisoned to NaN by one range test, the
+    // exp2 clamp is skipped; on positive normal inputs and |t| < 2040 it must agree bit for bit with the general form
+    for (double a0 : {0.0, -0.0, 1e-320, (double)INFINITY, (double)NAN, -1.0}) bad += !std::isnan(tab_log2<true>(a0, lg));
+    for (int i = 0; i < 200000; i++) {
+        double a = std::exp2(U(g) * 2040 - 1020) * (1 + U(g));
+        double L = tab_log2<true>(a, lg);
+        bad += !(L == tab_log2<false>(a, lg));
+        double T = -32.0 * 1.875 * U(g) * L;
+        bad += !(tab_exp2_32<true>(T, ex) == tab_exp2_32<false>(T, ex));
+    }
+    bad += !std::isnan(tab_exp2_32<true>(-27.2 * tab_log2<true>(0.0, lg), ex));
     printf("%.3e %.3e %.3e %d\n", maxl, maxe, maxh, bad);
     return 0;
 }

@@ -176,12 +176,16 @@ struct GenTables {
 template <int MODE, int E, int K0, int DK>
 __device__ __forceinline__ void weights(double d2, const KParams &p, const GenTables *gt, double (&h)[E]) {
     if constexpr (MODE == MODE_GEN) {
-        const double L = tab_log2(d2, gt->lg);
+        // K0 == 1 marks a pass whose exponents all satisfy 0 < p <= 3.75 (decided on the host): d2 = 0 may then be
+        // poisoned to NaN straight away (the cell is NaN in the reference too) and |c * L| < 2040 needs no clamp.
+        constexpr bool SAFE = (K0 == 1);
+        const double L = tab_log2<SAFE>(d2, gt->lg);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            // cexp holds 32 * (-p/2).  L is finite (saturating log2), so p == 0 gives 0 * L == 0 and exp2(0) == 1
-            // exactly: Go's Pow(d, -0) == 1 even at d == 0 needs no special case; d == 0 with p > 0 -> +inf.
-            h[e] = tab_exp2_32(p.cexp[e] * L, gt->ex);
+            // cexp holds 32 * (-p/2).  In the general form L is finite (saturating log2), so p == 0 gives 0 * L == 0
+            // and exp2(0) == 1 exactly: Go's Pow(d, -0) == 1 even at d == 0 needs no special case; d == 0 with
+            // p > 0 -> +inf -> NaN cell, p < 0 -> 0.
+            h[e] = tab_exp2_32<SAFE>(p.cexp[e] * L, gt->ex);
         }
     } else {
         double b = base_pow<MODE>(d2);

@@ -40,7 +40,11 @@ int plan_sweep(const double *exps, int n_exps, std::vector<Pass> &passes) {
             ps.mode = MODE_GEN;
             ps.first = e0;
             ps.count = len;
-            for (int i = 0; i < len; ++i) ps.cexp[i] = -exps[e0 + i] / 2.0;
+            ps.k0 = 1;  // "safe" pass: every exponent in (0, 3.75] (see weights<MODE_GEN>)
+            for (int i = 0; i < len; ++i) {
+                ps.cexp[i] = -exps[e0 + i] / 2.0;
+                if (!(exps[e0 + i] > 0.0 && exps[e0 + i] <= 3.75)) ps.k0 = 0;
+            }
             passes.push_back(ps);
             e0 += len;
         }
@@ -112,8 +116,7 @@ static const Variant kVariants[] = {
     V2R_TUNE("t384", MODE_RCP, 1, 4, 4, 1, 0, 384, 1), V2R_TUNE("t384", MODE_QRT, 1, 4, 4, 3, 0, 384, 1),
     V2R_TUNE("b2", MODE_RCP, 1, 4, 2, 1, 0, 256, 2), V2R_TUNE("b2", MODE_QRT, 9, 1, 2, 1, 1, 256, 2),
     V2R_TUNE("c1x4", MODE_QRT, 9, 1, 4, 1, 1, 256, 1), V2R_TUNE("c4x4", MODE_QRT, 1, 4, 4, 3, 0, 256, 1),
-    V2R_TUNE("g2x2", MODE_GEN, 1, 2, 2, 0, 0, 256, 2), V2R_TUNE("g4x4", MODE_GEN, 1, 4, 4, 0, 0, 256, 1),
-    V2R_TUNE("g1x2", MODE_GEN, 1, 1, 2, 0, 0, 256, 2),
+    V2R_TUNE("g2x2", MODE_GEN, 1, 2, 2, 1, 0, 256, 2), V2R_TUNE("g4x4", MODE_GEN, 1, 4, 4, 1, 0, 256, 1),
     Variant{MODE_RCP, 1, 1, 0, 6, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 6, 4, 1, 0, 256, 1, 1>, "MODE_RCP", true, "c6x4"},
     Variant{MODE_RCP, 1, 1, 0, 4, 6, 256, idw_fp64_kernel<MODE_RCP, 1, 4, 6, 1, 0, 256, 1, 1>, "MODE_RCP", true, "c4x6"},
     Variant{MODE_RCP, 1, 1, 0, 5, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 5, 4, 1, 0, 256, 1, 1>, "MODE_RCP", true, "c5x4"},
@@ -128,7 +131,13 @@ static const Variant kVariants[] = {
     V2R_VARIANT(MODE_QRT, 4, 2, 2, 2, 1, 256, 2),   // p = 1, 1.5, 2, 2.5       (config c5)
     // runtime ladders
     V2R_ROW(MODE_RCP), V2R_ROW(MODE_RSQ), V2R_ROW(MODE_QRT),
-    // general exponents: fewer cells per thread (log2/exp2 temporaries)
+    // general exponents, all in (0, 3.75]: no zero/overflow handling beyond one range test (K0 = 1 marks them)
+    V2R_VARIANT(MODE_GEN, 1, 2, 4, 1, 0, 256, 2), V2R_VARIANT(MODE_GEN, 2, 2, 2, 1, 0, 256, 2),
+    V2R_VARIANT(MODE_GEN, 3, 2, 2, 1, 0, 256, 2), V2R_VARIANT(MODE_GEN, 4, 2, 2, 1, 0, 256, 2),
+    V2R_VARIANT(MODE_GEN, 5, 2, 2, 1, 0, 256, 1), V2R_VARIANT(MODE_GEN, 6, 2, 2, 1, 0, 256, 1),
+    V2R_VARIANT(MODE_GEN, 7, 2, 2, 1, 0, 256, 1), V2R_VARIANT(MODE_GEN, 8, 2, 2, 1, 0, 256, 1),
+    V2R_VARIANT(MODE_GEN, 9, 2, 2, 1, 0, 256, 1), V2R_VARIANT(MODE_GEN, 10, 2, 2, 1, 0, 256, 1),
+    // general exponents, any value (p <= 0, large p): saturating log2 / clamped exp2
     V2R_VARIANT(MODE_GEN, 1, 2, 4, 0, 0, 256, 2), V2R_VARIANT(MODE_GEN, 2, 2, 2, 0, 0, 256, 2),
     V2R_VARIANT(MODE_GEN, 3, 2, 2, 0, 0, 256, 2), V2R_VARIANT(MODE_GEN, 4, 2, 2, 0, 0, 256, 2),
     V2R_VARIANT(MODE_GEN, 5, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE_GEN, 6, 2, 2, 0, 0, 256, 1),
@@ -147,8 +156,8 @@ static const Variant *pick_variant(const Pass &ps) {
         if (v.tag) continue;
         if (v.paired && !allow_paired) continue;
         if (v.mode != ps.mode || v.E != ps.count) continue;
-        if (ps.mode == MODE_GEN) return &v;
         if (v.k0 == ps.k0 && v.dk == ps.dk) return &v;
+        if (ps.mode == MODE_GEN) continue;
         if (v.k0 == 0 && !fallback) fallback = &v;
     }
     return fallback;
@@ -304,7 +313,8 @@ extern "C" int v2r_idw_describe(const double *exps, int n_exps, int precision, c
             if (!v) return set_error(V2R_IDW_EINVAL, "no kernel variant");
             char tmp[160];
             snprintf(tmp, sizeof tmp, "%sfp64/%s E=%d cells=%dx%d k0=%d dk=%d%s", s.empty() ? "" : " + ", mode_name(ps.mode),
-                     ps.count, v->cr, v->cc, ps.k0, ps.dk, v->tag ? v->tag : (v->paired ? " (paired reciprocal)" : (v->k0 ? " (static ladder)" : "")));
+                     ps.count, v->cr, v->cc, ps.k0, ps.dk,
+                     v->tag ? v->tag : (v->paired ? " (paired reciprocal)" : (ps.mode == MODE_GEN ? (v->k0 ? " (0 < p <= 3.75)" : " (any p)") : (v->k0 ? " (static ladder)" : ""))));
             s += tmp;
             ops += model_ops(ps, *v);
         }

@@ -77,6 +77,9 @@ __host__ __device__ inline void build_log_entry(int i, LogEntry &e) {
 __host__ __device__ inline double build_exp_entry(int j) { return exp2((double)j / kExpTab); }
 
 // log2(a) for a >= 0, SATURATING: a == 0 (or subnormal / negative) -> about -2^1000 (finite), +inf / NaN -> NaN.
+// POISON_ZERO (all exponents of the pass are > 0, where d2 = 0 makes the whole cell NaN anyway): zero, subnormal,
+// inf and NaN all give NaN, found with ONE unsigned range test.
+template <bool POISON_ZERO = false>
 __host__ __device__ __forceinline__ double tab_log2(double a, const LogEntry *tab) {
     const int hi = hi_word(a);
     const int k = (hi >> 20) - 1023;
@@ -91,18 +94,28 @@ __host__ __device__ __forceinline__ double tab_log2(double a, const LogEntry *ta
     q = fma(q, r, kLg[0]);
     const double L = fma(q, r, int2double(k) + t.log2_c);
     int lhi = hi_word(L);
-    if (hi < 0x00100000) lhi = (int)0xfe700000;   // zero / subnormal / negative: huge negative, finite
-    if (hi >= 0x7ff00000) lhi = 0x7ff80000;       // +inf / NaN: NaN
+    if constexpr (POISON_ZERO) {
+        if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) lhi = 0x7ff80000;  // not a positive normal number: NaN
+    } else {
+        if (hi < 0x00100000) lhi = (int)0xfe700000;   // zero / subnormal / negative: huge negative, finite
+        if (hi >= 0x7ff00000) lhi = 0x7ff80000;       // +inf / NaN: NaN
+    }
     return make_double(lhi, lo_word(L));
 }
 
 // 2^(T/32) for finite T (any magnitude) or NaN; the caller folds the factor 32 into its multiplier.
 // Saturates: T/32 >= 1024 -> +inf, T/32 <= -1075 -> 0.
+// BOUNDED: the caller guarantees |T/32| < 2040 or NaN (true when |p| <= 3.75: |log2 d2| <= 1075 for every positive
+// normal d2, and poisoned logs are NaN), so the clamp is skipped.
+template <bool BOUNDED = false>
 __host__ __device__ __forceinline__ double tab_exp2_32(double T, const double *tab) {
-    const int hi = hi_word(T);
-    // clamp 65280 <= |T| < inf (i.e. |T/32| >= 2040) to +-65280 with one unsigned range test; NaN passes through
-    const bool big = (unsigned)((hi & 0x7fffffff) - 0x40efe000) < (unsigned)(0x7ff00000 - 0x40efe000);
-    const double Tc = make_double(big ? ((hi & (int)0x80000000) | 0x40efe000) : hi, big ? 0 : lo_word(T));
+    double Tc = T;
+    if constexpr (!BOUNDED) {
+        // clamp 65280 <= |T| < inf (i.e. |T/32| >= 2040) to +-65280 with one unsigned range test; NaN passes through
+        const int hi = hi_word(T);
+        const bool big = (unsigned)((hi & 0x7fffffff) - 0x40efe000) < (unsigned)(0x7ff00000 - 0x40efe000);
+        Tc = make_double(big ? ((hi & (int)0x80000000) | 0x40efe000) : hi, big ? 0 : lo_word(T));
+    }
     const double Tn = Tc + kMagic;
     const int N = lo_word(Tn);                // nearest integer to T (two's complement in the low word)
     const double g = Tc - (Tn - kMagic);      // in [-1/2, 1/2], exact
