@@ -9,7 +9,7 @@ import re
 import subprocess
 import sys
 
-KEEP = re.compile(r"^(gpu__time_duration\.sum|dram__bytes_(read|write)\.sum|lts__t_bytes\.sum|lts__t_sectors_op_(read|write)\.sum|"
+KEEP = re.compile(r"^(gpu__time_duration\.sum|l1tex__m_xbar2l1tex_read_bytes\.sum|lts__t_sector_hit_rate\.pct|lts__t_sectors\.sum|dram__bytes_(read|write)\.sum|lts__t_bytes\.sum|lts__t_sectors_op_(read|write)\.sum|"
                   r"launch__(registers_per_thread|grid_size|block_size|occupancy_limit_\w+|waves_per_multiprocessor|shared_mem_per_block_static)|"
                   r"sm__warps_active\.avg\.pct_of_peak_sustained_active|sm__throughput\.avg\.pct_of_peak_sustained_elapsed|"
                   r"sm__inst_executed_pipe_(fp64|xu|fma|fmaheavy|fmalite|alu|lsu|uniform)\.avg\.pct_of_peak_sustained_(active|elapsed)|"

@@ -397,3 +397,34 @@ def test_randomized_grids_points_and_sweeps(ctx):
         for e, p in enumerate(exps):
             ref, scale = oracle_ref(ps, xi, yi, float(p))
             assert_parity(zs[e], ref, scale, what=f"random #{it} {rows}x{cols} n={n} step={step} p={p}")
+
+
+def test_stream_state_errors_and_reuse(ctx):
+    """call-sequence errors of the streaming API (V2R_IDW_ESTATE) and that a context is reusable afterwards"""
+    import ctypes as C
+    L = _lib.load()
+    ps, xi, yi = random_case(77, 300, 40, 50)
+    grid = make_grid(xi, yi)
+    h = ctx._h
+    r0, nr = C.c_int64(), C.c_int64()
+    buf = np.empty(2 * 16 * grid.cols)
+    assert L.v2r_idw_stream_next(h, C.c_void_p(buf.ctypes.data), C.byref(r0), C.byref(nr)) == _lib.ESTATE     # no session
+    assert L.v2r_idw_stream_end(h) == _lib.ESTATE
+    x, y, w = (np.ascontiguousarray(a) for a in (ps.x, ps.y, ps.w))
+    kr, kc = np.ascontiguousarray(ps.key_r), np.ascontiguousarray(ps.key_c)
+    exps = np.array([2.0, 3.0])
+    args = [h] + [C.c_void_p(a.ctypes.data) for a in (x, y, w, kr, kc)] + [len(x), C.byref(grid), C.c_void_p(exps.ctypes.data), 2, 0, 16]
+    assert L.v2r_idw_stream_begin(*args) == _lib.OK
+    assert L.v2r_idw_stream_begin(*args) == _lib.ESTATE                                                         # already open
+    with pytest.raises(_lib.IdwError):
+        ctx.solve(ps, grid, [2.0])                                                                              # solve during a session
+    got = np.full((2, grid.rows, grid.cols), np.nan)
+    while True:
+        assert L.v2r_idw_stream_next(h, C.c_void_p(buf.ctypes.data), C.byref(r0), C.byref(nr)) == _lib.OK
+        if nr.value == 0:
+            break
+        assert nr.value <= 16
+        got[:, r0.value:r0.value + nr.value] = buf[:2 * nr.value * grid.cols].reshape(2, nr.value, grid.cols)
+    assert L.v2r_idw_stream_next(h, C.c_void_p(buf.ctypes.data), C.byref(r0), C.byref(nr)) == _lib.OK and nr.value == 0  # stays finished
+    assert L.v2r_idw_stream_end(h) == _lib.OK
+    assert np.array_equal(got, ctx.solve(ps, grid, exps))                                                       # context still fine
