@@ -428,3 +428,33 @@ def test_stream_state_errors_and_reuse(ctx):
     assert L.v2r_idw_stream_next(h, C.c_void_p(buf.ctypes.data), C.byref(r0), C.byref(nr)) == _lib.OK and nr.value == 0  # stays finished
     assert L.v2r_idw_stream_end(h) == _lib.OK
     assert np.array_equal(got, ctx.solve(ps, grid, exps))                                                       # context still fine
+
+
+def test_callable_from_many_threads(ctx):
+    """cmd/idw.go:153-161 launches one goroutine per exponent and goroutines migrate between OS threads: the library
+    must be callable from any thread (explicit device per call, per-context mutex).  Eight threads hammer ONE context
+    and a second context concurrently; every raster must equal the one computed serially."""
+    import threading
+    ps, xi, yi = random_case(88, 800, 64, 96, step=2.0)
+    grid = make_grid(xi, yi)
+    exps = [0.5, 1.0, 1.5, 1.7, 2.0, 2.5, 3.0, 4.0]
+    want = [ctx.solve(ps, grid, [p])[0] for p in exps]
+    got, errs = [None] * len(exps), []
+    other = V.IdwContext(1)
+
+    def work(i):
+        try:
+            c = ctx if i % 2 == 0 else other
+            for _ in range(3):
+                got[i] = c.solve(ps, grid, [exps[i]])[0]
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(exps))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    other.close()
+    assert not errs, errs
+    for i in range(len(exps)):
+        assert np.array_equal(got[i], want[i]), exps[i]
