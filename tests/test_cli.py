@@ -105,3 +105,19 @@ def test_txt_100k_points_through_cli(tmp_path):
     rr, cc = np.arange(0, 256, 17), np.arange(3, 256, 19)[:16]
     ref = O.solve_cells(ops, O.Info(xi.min, xi.max, 100.0), O.Info(yi.min, yi.max, 100.0), 2.0, rr[:len(cc)], cc)
     assert np.max(np.abs(z[rr[:len(cc)], cc] - ref) / np.abs(ref)) < 2e-5
+
+
+def test_txt_reader_error_cases(tmp_path):
+    """read_data.go:17-111 failure modes: missing file, no ESTIMATE section, blank line, short point line, bad number"""
+    def plan(text):
+        f = tmp_path / "t.txt"
+        f.write_text(text)
+        return run("idw", "-f", str(f), "--plan", "-e", check=False)
+    assert "no such file" in run("idw", "-f", str(tmp_path / "missing.txt"), "--plan", check=False).stderr
+    assert "ESTIMATE not in file" in plan("POINTS 1\n1 2 3\n").stderr                       # read_data.go:89
+    assert "blank line" in plan("POINTS 1\n1 2 3\n\nESTIMATE\n0 5\n0 5").stderr              # the reference panics (:40)
+    assert "fewer than 3 fields" in plan("POINTS 2\n1 2 3\n4 5\nESTIMATE\n0 5\n0 5").stderr
+    assert "invalid syntax" in plan("POINTS 1\n1 2 3\nSTEP\nabc 1\nESTIMATE\n0 5\n0 5").stderr  # ParseFloat error is returned (:47-50)
+    ok = plan("POINTS 3\n1 2 3\r\n+4.5 5e0 x\n2 2 9\nSTEP\n0.5 0.25\nESTIMATE\n0 5\n0 5")   # CRLF, '+', exponent; 'x' -> 0 like the dropped error
+    p = json.loads(ok.stdout)
+    assert ok.returncode == 0 and (p["rows"], p["cols"], p["points_in"]) == (24, 12, 3)      # int((1+5)/0.25), int((1+5)/0.5)

@@ -140,6 +140,7 @@ int run_idw(int argc, char **argv) {
         idw::Options opt;
         opt.n_gpus = (int)F.gpus;
         opt.fp32 = F.fp32;
+        opt.progress = [](const std::string &m) { info(m); };
         int64_t band = 0;
         if (F.useChunking) {  // ChunkSolve semantics: --cy is the streamed band height (idw_chunk.go:48-53 for oversize chunks)
             band = F.idwChunkY;

@@ -167,10 +167,17 @@ void SweepSolve(const tools::PointSet &data, const std::vector<std::string> &out
     std::vector<char> created(E, 0);
     if (rows == 0 || cols == 0)
         for (int e = 0; e < E; ++e) processing::WriteGDAL(out, gd, outfiles[e], {0, 0}, {rows, cols}, {0, 0}, true);
+    // progress like ChunkSolve's "~10%, i / total" lines (features/idw/idw_chunk.go:77,92-96), per streamed band
+    const int64_t total_bands = std::max<int64_t>(1, (rows + band - 1) / band);
+    const int64_t progress = std::max<int64_t>(1, total_bands / 10);
+    int64_t done = 0;
     for (;;) {
         int64_t r0 = 0, nr = 0;
         check(v2r_idw_stream_next(ctx, out, &r0, &nr), "v2r_idw_stream_next");
         if (nr == 0) break;
+        if (opt.progress && bandRows > 0 && ++done % progress == 0)
+            opt.progress("~" + std::to_string(std::min<int64_t>(100, 100 * done / total_bands)) + "%, " + std::to_string(done) + " / " +
+                         std::to_string(total_bands));
         const int64_t plane = nr * cols;
         for (int e = 0; e < E; ++e) {  // the next band is already computing while these windows are written
             processing::WriteGDAL(out + (int64_t)e * plane, gd, outfiles[e], {r0, 0}, {rows, cols}, {nr, cols}, !created[e]);

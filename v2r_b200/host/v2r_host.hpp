@@ -89,8 +89,12 @@ void TransferType(const std::string &src, const std::string &dst, const std::str
 
 namespace idw {
 
-struct Options { int n_gpus = 1; bool fp32 = false; };
 using Channel = std::function<void(const std::string &)>;  // `channel <- msg`
+struct Options {
+    int n_gpus = 1;
+    bool fp32 = false;
+    Channel progress;  // optional: receives ChunkSolve-style "~40%, 8 / 21" lines while bands stream out
+};
 
 // One context per process (lazy).  Throws v2r::Error with the library's message on failure.
 v2r_idw_ctx *Context(const Options &opt);
