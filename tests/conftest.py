@@ -17,3 +17,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """A fresh checkout has no binaries (they are git-ignored): build the library, the CLI and the oracle once."""
+    lib = os.path.join(ROOT, "v2r_b200", "lib", "libv2r_idw.so")
+    cli = os.path.join(ROOT, "v2r_b200", "bin", "v2r")
+    if not (os.path.exists(lib) and os.path.exists(cli)):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "v2r_b200", "csrc"), "-j4", "-s"])

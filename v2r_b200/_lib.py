@@ -74,8 +74,12 @@ def load():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                              "(nvcc, sm_100a).  v2r_b200 has no CPU fallback.")
+            try:  # a fresh checkout: compile it (nvcc cross-compiles sm_100a without a GPU); never a substitute path
+                build()
+            except Exception as e:  # noqa: BLE001
+                raise ImportError(f"{LIB_PATH} is missing and could not be built ({e}): run "
+                                  "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a).  "
+                                  "v2r_b200 has no CPU fallback.") from e
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)  # AttributeError if the ABI lost a symbol
