@@ -80,10 +80,20 @@ def cpu_sample(name, seconds, scale_rows=1):
             O.chunk_solve_rows(ps, oi(xi), oi(yi), rows, cols, 0, nrows, 1, chunk_c, float(p), threads)
         return time.perf_counter() - t0
 
+    def run_serial(ncells=256):
+        # FullSolve semantics (features/idw/idw.go:34-40): one thread walks the cells of row 0 in order
+        cc = np.arange(min(ncells, cols), dtype=np.int64)
+        t0 = time.perf_counter()
+        for p in exps:
+            O.solve_cells(ps, oi(xi), oi(yi), float(p), np.zeros_like(cc), cc, nthreads=1)
+        dt = time.perf_counter() - t0
+        return {"value": float(len(cc)) * n / dt / 1e9, "unit": UNIT, "cores": 1,
+                "sample": f"first {len(cc)} cells of row 0 x {n} points x {E} exponent(s), oracle port of FullSolve, {dt:.1f} s"}
+
     t = run(1)  # calibrate on one row, then size the sample for ~`seconds`
     nrows = int(max(1, min(rows, seconds / max(t, 1e-6))))
-    return dict(run=lambda: run(nrows), evals=float(nrows) * cols * n, E=E, threads=threads, nrows=nrows,
-                cols=cols, n=n, calib_s=t)
+    return dict(run=lambda: run(nrows), run_serial=run_serial, evals=float(nrows) * cols * n, E=E, threads=threads,
+                nrows=nrows, cols=cols, n=n, calib_s=t)
 
 
 def reference_arm(args):
@@ -104,7 +114,8 @@ def reference_arm(args):
         "warmup": min(args.warmup, 1), "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": _workload_name(args.workload, 1), "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": s["threads"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": s["threads"], "kind": "port", "sample": sample,
+                         "serial": s["run_serial"]()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
     return 0
@@ -326,7 +337,8 @@ def ours(args):
             tc = s["run"]()
             cpu = {"value": s["evals"] / tc / 1e9, "unit": UNIT, "cores": s["threads"], "kind": "port",
                    "sample": f"rows [0,{s['nrows']}) x {s['cols']} cols x {s['n']} points x {s['E']} exponent(s) of {args.workload}, "
-                             f"oracle port of ChunkSolve (1-row chunks), {tc:.1f} s"}
+                             f"oracle port of ChunkSolve (1-row chunks), {tc:.1f} s",
+                   "serial": s["run_serial"]()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
