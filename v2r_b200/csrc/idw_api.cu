@@ -489,15 +489,17 @@ int v2r_idw_init(int n_gpus, v2r_idw_ctx **out) {
     if (!out) return set_error(V2R_IDW_EINVAL, "out is NULL");
     *out = nullptr;
     if (n_gpus != 1 && n_gpus != 2 && n_gpus != 4 && n_gpus != 8) return set_error(V2R_IDW_EINVAL, "n_gpus must be 1, 2, 4 or 8 (got %d)", n_gpus);
-    std::vector<int> devs(n_gpus);
-    for (int i = 0; i < n_gpus; ++i) devs[i] = i;
-    return create_ctx(devs, out);
+    return guarded([&] {
+        std::vector<int> devs(n_gpus);
+        for (int i = 0; i < n_gpus; ++i) devs[i] = i;
+        return create_ctx(devs, out);
+    });
 }
 
 int v2r_idw_init_device(int device, v2r_idw_ctx **out) {
     if (!out) return set_error(V2R_IDW_EINVAL, "out is NULL");
     *out = nullptr;
-    return create_ctx({device}, out);
+    return guarded([&] { return create_ctx({device}, out); });
 }
 
 void v2r_idw_destroy(v2r_idw_ctx *ctx) {
@@ -622,16 +624,18 @@ int v2r_idw_solve_rows(v2r_idw_ctx *ctx, const double *x, const double *y, const
     if (!ctx) return set_error(V2R_IDW_EINVAL, "ctx is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (grid && nrows > 0 && grid->cols > 0 && !out) return set_error(V2R_IDW_EINVAL, "out is NULL");
-    int rc = begin_session(ctx, x, y, z, key_r, key_c, n, grid, row0, nrows, exps, n_exps, precision, 0);
-    if (rc) return rc;
-    const long long plane = (long long)nrows * grid->cols;
-    for (;;) {
-        long long r0 = 0, nr = 0;
-        rc = next_band(ctx, out, plane, false, &r0, &nr);
-        if (rc || nr == 0) break;
-    }
-    int rc2 = end_session(ctx);
-    return rc ? rc : rc2;
+    return guarded([&] {
+        int rc = begin_session(ctx, x, y, z, key_r, key_c, n, grid, row0, nrows, exps, n_exps, precision, 0);
+        if (rc) return rc;
+        const long long plane = (long long)nrows * grid->cols;
+        for (;;) {
+            long long r0 = 0, nr = 0;
+            rc = next_band(ctx, out, plane, false, &r0, &nr);
+            if (rc || nr == 0) break;
+        }
+        int rc2 = end_session(ctx);
+        return rc ? rc : rc2;
+    });
 }
 
 int v2r_idw_solve(v2r_idw_ctx *ctx, const double *x, const double *y, const double *z, const int64_t *key_r,
@@ -648,7 +652,7 @@ int v2r_idw_stream_begin(v2r_idw_ctx *ctx, const double *x, const double *y, con
     if (!grid) return set_error(V2R_IDW_EINVAL, "grid is NULL");
     if (band_rows < 0) return set_error(V2R_IDW_EINVAL, "band_rows < 0");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    return begin_session(ctx, x, y, z, key_r, key_c, n, grid, 0, grid->rows, exps, n_exps, precision, band_rows);
+    return guarded([&] { return begin_session(ctx, x, y, z, key_r, key_c, n, grid, 0, grid->rows, exps, n_exps, precision, band_rows); });
 }
 
 int v2r_idw_stream_next(v2r_idw_ctx *ctx, double *out, int64_t *row0, int64_t *nrows) {
@@ -657,7 +661,7 @@ int v2r_idw_stream_next(v2r_idw_ctx *ctx, double *out, int64_t *row0, int64_t *n
     if (!out && ctx->ses.active && ctx->ses.cur_round < ctx->ses.rounds && ctx->ses.grid.cols > 0)
         return set_error(V2R_IDW_EINVAL, "out is NULL");
     long long r0 = 0, nr = 0;
-    int rc = next_band(ctx, out, 0, true, &r0, &nr);
+    int rc = guarded([&] { return next_band(ctx, out, 0, true, &r0, &nr); });
     *row0 = r0;
     *nrows = nr;
     return rc;

@@ -2,6 +2,8 @@
 #pragma once
 #include <atomic>
 #include <cstdarg>
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -21,6 +23,21 @@ struct Pass {
 
 int set_error(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 const char *last_error();
+
+// Nothing may unwind across the C ABI (cgo would abort the Go process): every entry point that can allocate runs
+// its body through this.
+template <typename F>
+int guarded(F &&body) noexcept {
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        return set_error(V2R_IDW_ENOMEM, "out of host memory");
+    } catch (const std::exception &e) {
+        return set_error(V2R_IDW_EINVAL, "internal error: %s", e.what());
+    } catch (...) {
+        return set_error(V2R_IDW_EINVAL, "internal error");
+    }
+}
 
 int plan_sweep(const double *exps, int n_exps, std::vector<Pass> &passes);
 int validate_geometry(long long n, const v2r_idw_grid *g, long long row0, long long nrows, int n_exps);

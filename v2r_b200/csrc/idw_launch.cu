@@ -291,15 +291,18 @@ extern "C" int v2r_idw_launch_rows(int device, void *stream, const double *d_x, 
     if (nrows == 0 || grid->cols == 0) return V2R_IDW_OK;
     cudaError_t ce = cudaSetDevice(device);
     if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(ce));
-    if (precision == V2R_IDW_FP32)
-        return launch_rows_fp32((cudaStream_t)stream, d_x, d_y, d_z, (const long long *)d_key_r, (const long long *)d_key_c, n,
+    return guarded([&] {
+        if (precision == V2R_IDW_FP32)
+            return launch_rows_fp32((cudaStream_t)stream, d_x, d_y, d_z, (const long long *)d_key_r, (const long long *)d_key_c, n,
+                                    *grid, row0, nrows, exps, n_exps, d_out);
+        return launch_rows_fp64((cudaStream_t)stream, d_x, d_y, d_z, (const long long *)d_key_r, (const long long *)d_key_c, n,
                                 *grid, row0, nrows, exps, n_exps, d_out);
-    return launch_rows_fp64((cudaStream_t)stream, d_x, d_y, d_z, (const long long *)d_key_r, (const long long *)d_key_c, n,
-                            *grid, row0, nrows, exps, n_exps, d_out);
+    });
 }
 
 extern "C" int v2r_idw_describe(const double *exps, int n_exps, int precision, char *buf, size_t buf_len,
                                 double *fp64_ops_per_pair) {
+  return guarded([&] {
     std::vector<Pass> passes;
     int rc = plan_sweep(exps, n_exps, passes);
     if (rc) return rc;
@@ -324,7 +327,8 @@ extern "C" int v2r_idw_describe(const double *exps, int n_exps, int precision, c
         buf[buf_len - 1] = 0;
     }
     if (fp64_ops_per_pair) *fp64_ops_per_pair = ops;
-    return V2R_IDW_OK;
+    return (int)V2R_IDW_OK;
+  });
 }
 
 // ------------------------------------------------------------------------------------------
