@@ -121,3 +121,34 @@ def test_txt_reader_error_cases(tmp_path):
     ok = plan("POINTS 3\n1 2 3\r\n+4.5 5e0 x\n2 2 9\nSTEP\n0.5 0.25\nESTIMATE\n0 5\n0 5")   # CRLF, '+', exponent; 'x' -> 0 like the dropped error
     p = json.loads(ok.stdout)
     assert ok.returncode == 0 and (p["rows"], p["cols"], p["points_in"]) == (24, 12, 3)      # int((1+5)/0.25), int((1+5)/0.5)
+
+
+def test_cpp_readers_parse_bit_exactly_and_dedupe_like_the_oracle(tmp_path):
+    """the in-place tokenizer (std::from_chars) must give the doubles Python's float() gives for every spelling, and
+    MakeCoordSpace through the C++ host must equal the oracle's input-order restatement (tools/utils.go:97-119)"""
+    rng = np.random.default_rng(5)
+    n = 400
+    x, y = rng.uniform(-50, 1050, n), rng.uniform(-20, 520, n)
+    w = rng.normal(0, 1e3, n)
+    fmts = [repr, lambda v: f"{v:.3f}", lambda v: f"{v:.10e}", lambda v: f"{v:+.6f}", lambda v: f"{v:.17g}", lambda v: str(int(v))]
+    lines, want = [], []
+    for i in range(n):
+        f = fmts[i % len(fmts)]
+        toks = [f(float(x[i])), f(float(y[i])), f(float(w[i]))]
+        lines.append("  ".join(toks) if i % 7 else "\t".join(toks) + " ")
+        want.append([float(t) for t in toks])
+    path = tmp_path / "pts.txt"
+    path.write_text(f"POINTS {n}\n" + "\n".join(lines) + "\nSTEP\n10 5\nESTIMATE\n0 1000\n0 500\n")
+    p = json.loads(run("idw", "-f", str(path), "--plan", "-e", "--dump-points", str(n)).stdout)
+    assert p["raw"] == want
+    wx, wy, ww = (np.array([r[k] for r in want]) for k in range(3))
+    ops = O.make_coord_space(wx, wy, ww, O.Info(0, 1000, 10.0), O.Info(0, 500, 5.0))
+    assert p["points"] == len(ops) < n
+    keyed = np.array(p["keyed"])
+    assert np.array_equal(keyed[:, 0], ops.x) and np.array_equal(keyed[:, 2], ops.w)
+    assert np.array_equal(keyed[:, 3].astype(np.int64), ops.key_r) and np.array_equal(keyed[:, 4].astype(np.int64), ops.key_c)
+    # the gpkg reader against the 14 exact points of tools/processing/gpkg_test.go:12-27
+    exp = json.load(open(os.path.join(GOLDEN, "gpkg_points.json")))
+    g = json.loads(run("idw", "-g", "-f", os.path.join(GOLDEN, "input.gpkg"), "--layer", "wsels", "--field", "elevation", "--sx", "1",
+                       "--sy", "2", "--plan", "-e", "--dump-points", "14").stdout)
+    assert g["raw"] == exp["points"]

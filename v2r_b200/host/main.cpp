@@ -35,6 +35,7 @@ void debug(const std::string &m) { logf(2, "DEBUG", m); }
 
 struct Flags {
     bool fromGPKG = false, useChunking = false, fp32 = false, plan = false;
+    long dumpPoints = 0;  // --dump-points N: print the first N parsed points (%.17g) with --plan; a test hook for the readers
     long idwChunkX = 200, idwChunkY = 200, epsg = 2284, gpus = 1;
     double expIncrement = .5, expStart = 1.5, expEnd = 0.0, stepX = 100.0, stepY = 100.0;
     bool eeChanged = false;
@@ -66,6 +67,7 @@ int run_idw(int argc, char **argv) {
         else if (a == "--concurrent") F.useChunking = boolean();
         else if (a == "--fp32") F.fp32 = boolean();
         else if (a == "--plan") F.plan = boolean();
+        else if (a == "--dump-points") F.dumpPoints = atol(need().c_str());
         else if (a == "--debug") { if (boolean()) g_level = 2; }
         else if (a == "--error") { if (boolean() && g_level != 2) g_level = 0; }
         else if (a == "--log") { (void)boolean(); }  // lumberjack file logging: host plumbing, not reproduced
@@ -133,8 +135,18 @@ int run_idw(int argc, char **argv) {
             double ops = 0;
             if (v2r_idw_describe(pows.data(), (int)pows.size(), F.fp32 ? V2R_IDW_FP32 : V2R_IDW_FP64, buf, sizeof buf, &ops) != V2R_IDW_OK)
                 fatal(v2r_idw_last_error());
-            printf("{\"rows\": %lld, \"cols\": %lld, \"points_in\": %lld, \"points\": %lld, \"exponents\": %zu, \"kernel\": \"%s\", \"first_outfile\": \"%s\"}\n",
+            printf("{\"rows\": %lld, \"cols\": %lld, \"points_in\": %lld, \"points\": %lld, \"exponents\": %zu, \"kernel\": \"%s\", \"first_outfile\": \"%s\"",
                    (long long)rows, (long long)cols, (long long)rd.points.size(), (long long)data.size(), pows.size(), buf, outs[0].c_str());
+            if (F.dumpPoints > 0) {  // the raw reader output (before MakeCoordSpace), then the keyed set
+                printf(", \"raw\": [");
+                for (int64_t i = 0; i < rd.points.size() && i < F.dumpPoints; ++i)
+                    printf("%s[%.17g, %.17g, %.17g]", i ? ", " : "", rd.points.x[i], rd.points.y[i], rd.points.w[i]);
+                printf("], \"keyed\": [");
+                for (int64_t i = 0; i < data.size() && i < F.dumpPoints; ++i)
+                    printf("%s[%.17g, %.17g, %.17g, %lld, %lld]", i ? ", " : "", data.x[i], data.y[i], data.w[i], (long long)data.key_r[i], (long long)data.key_c[i]);
+                printf("]");
+            }
+            printf("}\n");
             return 0;
         }
         idw::Options opt;
