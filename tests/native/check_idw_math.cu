@@ -54,6 +54,21 @@ int main() {
         bad += !(tab_exp2_32<true>(T, ex) == tab_exp2_32<false>(T, ex));
     }
     bad += !std::isnan(tab_exp2_32<true>(-27.2 * tab_log2<true>(0.0, lg), ex));
+    // base powers of the rcp / rsqrt / root4 classes: a ~2^-20 seed (emulated on the host by truncating operand and
+    // result to their high words, the documented behaviour of MUFU.RCP64H / RSQ64H) plus ONE cubic step must reach
+    // a few ulp; worst-case seeds are covered by sampling mantissas whose low words are all ones
+    double max1 = 0, max12 = 0, max14 = 0;
+    for (long i = 0; i < 2000000; i++) {
+        double a = std::exp2(U(g) * 400 - 200) * (1 + U(g));
+        if (i % 3 == 0) a = make_double(hi_word(a), (int)0xffffffff);   // largest truncation error of the seed operand
+        long double t1 = 1.0L / a, t12 = 1.0L / sqrtl(a), t14 = 1.0L / sqrtl(sqrtl(a));
+        max1 = fmax(max1, fabs((double)((pow_m1(a) - t1) / t1)));
+        max12 = fmax(max12, fabs((double)((pow_m12(a) - t12) / t12)));
+        max14 = fmax(max14, fabs((double)((pow_m14(a) - t14) / t14)));
+    }
+    bad += !(max1 < 4e-16) + !(max12 < 6e-16) + !(max14 < 8e-16);
+    bad += !std::isnan(pow_m1(0.0)) + !std::isnan(pow_m12(0.0)) + !std::isnan(pow_m14(0.0));   // d = 0 off-key -> NaN cell
+    fprintf(stderr, "base powers: max rel err rcp %.2e rsqrt %.2e root4 %.2e\n", max1, max12, max14);
     printf("%.3e %.3e %.3e %d\n", maxl, maxe, maxh, bad);
     return 0;
 }

@@ -83,49 +83,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                  : "memory");
 }
 
-// MUFU.RCP64H / MUFU.RSQ64H: ~2^-20 relative seeds computed from the high word of the operand.
-__device__ __forceinline__ double rcp_seed(double a) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-    return r;
-}
-__device__ __forceinline__ double rsq_seed(double a) {
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-    return r;
-}
-
-// ---------------------------------------------------------------------------- base powers
-// 1/a: seed + one cubic step (e = 1 - a r0 ; r = r0 (1 + e + e^2)); truncation e^3 ~ 2^-60.
-// 3 FP64-pipe instructions + 1 MUFU.  a = 0 -> NaN (reference: +Inf weight -> Inf/Inf = NaN cell).
-__device__ __forceinline__ double pow_m1(double a) {
-    double r0 = rcp_seed(a);
-    double e = fma(-a, r0, 1.0);
-    double t = fma(e, e, e);
-    return fma(r0, t, r0);
-}
-// a^(-1/2): e = 1 - a y0^2 ; y = y0 (1 + e/2 + 3 e^2/8).  5 FP64 + 1 MUFU.
-__device__ __forceinline__ double pow_m12(double a) {
-    double y0 = rsq_seed(a);
-    double t = a * y0;
-    double e = fma(-t, y0, 1.0);
-    double p = fma(e, 0.375, 0.5);
-    double ye = y0 * e;
-    return fma(ye, p, y0);
-}
-// a^(-1/4): q0 = rsq(a) * rsq(rsq(a)); e = 1 - a q0^4 ; q = q0 (1 + e/4 + 5 e^2/32).  7 FP64 + 2 MUFU.
-__device__ __forceinline__ double pow_m14(double a) {
-    double y0 = rsq_seed(a);   // a^-1/2 (low word 0, so the second seed sees it exactly)
-    double z0 = rsq_seed(y0);  // a^+1/4
-    double q0 = y0 * z0;       // a^-1/4, ~2^-20
-    double q2 = q0 * q0;
-    double t = a * q2;
-    double e = fma(-t, q2, 1.0);
-    double p = fma(e, 0.15625, 0.25);
-    double qe = q0 * e;
-    return fma(qe, p, q0);
-}
-
 // b^K as a balanced product b^(K/2) * b^(K - K/2): depth log2 K instead of K.  In a sweep every exponent calls
 // this with its own K; the common sub-powers are merged by the compiler (pure FP multiplies of identical
 // operands), so consecutive powers 1..9 still cost 8 multiplies but the dependent chain is 4 deep, not 8.

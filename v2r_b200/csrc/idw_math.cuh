@@ -1,4 +1,5 @@
-// idw_math.cuh -- software log2 / exp2 for the `general` exponent class (h = exp2(c * log2 d2)).
+// idw_math.cuh -- the arithmetic of d2^(-p/2): seed-plus-one-cubic-step base powers of the rcp / rsqrt / root4 classes
+// (bottom of the file) and software log2 / exp2 for the `general` class (h = exp2(c * log2 d2)).
 //
 // The FP64 pipe is the bottleneck of every IDW kernel, so these are written for the fewest FP64-pipe
 // instructions that still give ~1e-15: table-driven argument reduction (tables live in shared memory, built once
@@ -133,6 +134,59 @@ __host__ __device__ __forceinline__ double tab_exp2_32(double T, const double *t
     // multiplies themselves; the first factor rides on the table value's exponent field (an integer add)
     const double s1 = make_double(hi_word(e) + (n1 << 20), lo_word(e));
     return (p * s1) * make_double((n2 + 1023) << 20, 0);
+}
+
+// MUFU.RCP64H / MUFU.RSQ64H: ~2^-20 relative seeds computed from the high word of the operand.
+// The host versions emulate the documented behaviour (operand and result truncated to their high words, i.e.
+// 20 mantissa bits) so tests/ can check the refinement steps below against libm on the CPU.
+__host__ __device__ __forceinline__ double rcp_seed(double a) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    return r;
+#else
+    return make_double(hi_word(1.0 / make_double(hi_word(a), 0)), 0);
+#endif
+}
+__host__ __device__ __forceinline__ double rsq_seed(double a) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    return r;
+#else
+    return make_double(hi_word(1.0 / sqrt(make_double(hi_word(a), 0))), 0);
+#endif
+}
+
+// ---------------------------------------------------------------------------- base powers
+// 1/a: seed + one cubic step (e = 1 - a r0 ; r = r0 (1 + e + e^2)); truncation e^3 ~ 2^-60.
+// 3 FP64-pipe instructions + 1 MUFU.  a = 0 -> NaN (reference: +Inf weight -> Inf/Inf = NaN cell).
+__host__ __device__ __forceinline__ double pow_m1(double a) {
+    double r0 = rcp_seed(a);
+    double e = fma(-a, r0, 1.0);
+    double t = fma(e, e, e);
+    return fma(r0, t, r0);
+}
+// a^(-1/2): e = 1 - a y0^2 ; y = y0 (1 + e/2 + 3 e^2/8).  5 FP64 + 1 MUFU.
+__host__ __device__ __forceinline__ double pow_m12(double a) {
+    double y0 = rsq_seed(a);
+    double t = a * y0;
+    double e = fma(-t, y0, 1.0);
+    double p = fma(e, 0.375, 0.5);
+    double ye = y0 * e;
+    return fma(ye, p, y0);
+}
+// a^(-1/4): q0 = rsq(a) * rsq(rsq(a)); e = 1 - a q0^4 ; q = q0 (1 + e/4 + 5 e^2/32).  7 FP64 + 2 MUFU.
+__host__ __device__ __forceinline__ double pow_m14(double a) {
+    double y0 = rsq_seed(a);   // a^-1/2 (low word 0, so the second seed sees it exactly)
+    double z0 = rsq_seed(y0);  // a^+1/4
+    double q0 = y0 * z0;       // a^-1/4, ~2^-20
+    double q2 = q0 * q0;
+    double t = a * q2;
+    double e = fma(-t, q2, 1.0);
+    double p = fma(e, 0.15625, 0.25);
+    double qe = q0 * e;
+    return fma(qe, p, q0);
 }
 
 }  // namespace v2r
