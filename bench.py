@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- IDW gridding throughput on B200 (BASELINE.json metric: G cell*point evals/s, FP64).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--precision fp64|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c3|c5] [--precision fp64|fp32]
     python bench.py --impl reference ...        # the reference's CPU algorithm (oracle port) on the host cores
     torchrun ... bench.py --gpus N ...          # one rank per GPU (the driver's launch for N > 1)
 
-A step = one pass of the hot path (every cell of this rank's row band x every point x all exponents of
-the workload) on synthetic data of the named shape.  `value` is the whole-job throughput with inputs
-resident in HBM (CUDA events on the launching stream, max over ranks); `e2e` is the same metric
-through the C ABI with HOST buffers (v2r_idw_solve: H2D of the points, kernels, gather, D2H of the
-rasters all inside the timed region).  Weak scaling: every rank keeps one workload-sized row band
-(the grid grows by N in y), no data-path collective in the timed region -- the point broadcast and
-band gather belong to e2e.  See DESIGN.md section 6 for the roofline arithmetic.
+Default workload = the configuration north_star states its target on: the c4 point set (1 M clustered points, 967 k
+after dedupe) on the 16384-column grid, p = 2, FP64 -- a fixed slab of 2048 full-width rows [7168, 9216) of the
+16384 x 16384 grid (the whole grid is 102 s per step on one GPU; the slab is 1/8 of it), STRONG-scaled: the slab is
+split into N contiguous row bands, one per GPU.
+
+A step = one pass of the hot path (every cell of this rank's row band x every point x all exponents of the
+workload).  `value` is the whole-job throughput with inputs resident in HBM (CUDA events on the launching stream
+around v2r_idw_launch_rows, max over ranks); `e2e` is the same metric through the C ABI with HOST buffers
+(v2r_idw_solve_rows on one context driving all N GPUs: H2D of the points, NCCL broadcast, kernels, per-device D2H of
+the bands into the pinned host raster, all inside the timed region).  `parity` is checked inside the bench on the
+e2e raster: bit-equality with a 1-GPU solve of the same slab, >= 2000 oracle spot cells at 1e-12 and all in-slab
+exact-hit cells bit-equal.  See DESIGN.md section 6 for the roofline arithmetic.
 """
 from __future__ import annotations
 
@@ -34,6 +39,9 @@ UNIT = "G evals/s"
 NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 FP64 lanes x 2 x 1.965 GHz
 # algorithmic FP64-pipe instruction slots per cell-point pair
 ALGO_SLOTS = {"c2": 8.0, "c3": 38.0, "c4": 8.0, "c5": 24.0}
+# default slab (first row, rows) of each workload's grid; None = the whole grid
+SLABS = {"c4": (7168, 2048), "c2": None, "c3": None, "c5": None}
+REL64, REL32 = 1e-12, 2e-5
 
 
 def parse():
@@ -42,29 +50,50 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
-    ap.add_argument("--band-rows", type=int, default=0, help="rows of the rank's band per step (0 = the whole workload grid)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: every rank keeps one workload-sized band (grid grows with N); strong: the workload's own grid is split into N row bands")
-    ap.add_argument("--exps", default="", help="comma list overriding the workload's exponent sweep (diagnostics)")
+    ap.add_argument("--slab", default="", help="R0:NROWS rows of the workload grid that make up the job (default: c4 7168:2048, others whole grid)")
+    ap.add_argument("--band-rows", type=int, default=0, help="diagnostics: rows of the rank's band per step (0 = the rank's whole share)")
+    ap.add_argument("--scaling", default="", choices=["", "weak", "strong"],
+                    help="strong (default): the job's rows are split into N row bands; weak: every rank keeps one job-sized band (grid grows with N)")
+    ap.add_argument("--exps", default="", help="comma list overriding the workload's exponent sweep (diagnostics; roofline.frac becomes null)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-cells", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if not a.scaling:
+        a.scaling = "strong"
+    return a
+
+
+def job_rows(args, grid_rows):
+    """(first row, rows) of the job inside the workload's grid"""
+    if args.slab:
+        r0, nr = (int(v) for v in args.slab.split(":"))
+    elif SLABS[args.workload] and args.scaling == "strong":
+        r0, nr = SLABS[args.workload]
+    else:
+        r0, nr = 0, grid_rows
+    r0 = max(0, min(r0, grid_rows))
+    return r0, max(0, min(nr, grid_rows - r0))
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_sample(name, seconds, scale_rows=1):
+def cpu_sample(args, seconds):
     """Times the oracle (CPU restatement of the reference, `-c` concurrent mode) on a bounded sample of
-    the workload: rows [0, R) of the same grid against the full point set, all host threads."""
+    the workload: the first rows of the job against the full point set, all host threads."""
     from oracle import oracle as O
     from v2r_b200 import workloads
-    x, y, w, xi, yi, exps = workloads.make(name, scale_rows=scale_rows)
+    x, y, w, xi, yi, exps = workloads.make(args.workload)
+    if args.exps:
+        exps = np.array([float(v) for v in args.exps.split(",")])
     oi = lambda i: O.Info(i.min, i.max, i.step)  # noqa: E731
     ps = O.make_coord_space(x, y, w, oi(xi), oi(yi))
     rows, cols = O.get_dimensions(oi(xi), oi(yi))
+    jr0, jnr = job_rows(args, rows)
     threads = O.num_threads()
     n = len(ps)
     E = len(exps)
@@ -77,43 +106,47 @@ def cpu_sample(name, seconds, scale_rows=1):
         t0 = time.perf_counter()
         # the reference runs one goroutine per exponent (cmd/idw.go:153-161), each a full ChunkSolve
         for p in exps:
-            O.chunk_solve_rows(ps, oi(xi), oi(yi), rows, cols, 0, nrows, 1, chunk_c, float(p), threads)
+            O.chunk_solve_rows(ps, oi(xi), oi(yi), rows, cols, jr0, nrows, 1, chunk_c, float(p), threads)
         return time.perf_counter() - t0
 
-    def run_serial(ncells=256):
-        # FullSolve semantics (features/idw/idw.go:34-40): one thread walks the cells of row 0 in order
+    def run_serial(ncells=64):
+        # FullSolve semantics (features/idw/idw.go:34-40): one thread walks the cells of a row in order
         cc = np.arange(min(ncells, cols), dtype=np.int64)
         t0 = time.perf_counter()
         for p in exps:
-            O.solve_cells(ps, oi(xi), oi(yi), float(p), np.zeros_like(cc), cc, nthreads=1)
+            O.solve_cells(ps, oi(xi), oi(yi), float(p), np.full_like(cc, jr0), cc, nthreads=1)
         dt = time.perf_counter() - t0
         return {"value": float(len(cc)) * n / dt / 1e9, "unit": UNIT, "cores": 1,
-                "sample": f"first {len(cc)} cells of row 0 x {n} points x {E} exponent(s), oracle port of FullSolve, {dt:.1f} s"}
+                "sample": f"first {len(cc)} cells of row {jr0} x {n} points x {E} exponent(s), oracle port of FullSolve, {dt:.1f} s"}
 
-    t = run(1)  # calibrate on one row, then size the sample for ~`seconds`
-    nrows = int(max(1, min(rows, seconds / max(t, 1e-6))))
+    # calibrate on a strip of one row, then size the sample for ~`seconds`
+    t0 = time.perf_counter()
+    cal_cells = min(cols, 512)
+    O.solve_cells(ps, oi(xi), oi(yi), float(exps[0]), np.full(cal_cells, jr0, np.int64), np.arange(cal_cells, dtype=np.int64))
+    t_row = (time.perf_counter() - t0) * cols / cal_cells * E
+    nrows = int(max(1, min(jnr, seconds / max(t_row, 1e-6))))
     return dict(run=lambda: run(nrows), run_serial=run_serial, evals=float(nrows) * cols * n, E=E, threads=threads,
-                nrows=nrows, cols=cols, n=n, calib_s=t)
+                nrows=nrows, cols=cols, n=n, row0=jr0)
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    s = cpu_sample(args.workload, args.cpu_seconds)
+    s = cpu_sample(args, args.cpu_seconds)
     for _ in range(min(args.warmup, 1)):  # CPU code has no clocks to warm; one pass touches the pages
         s["run"]()
     t = 0.0
     for _ in range(args.steps):
         t += s["run"]()
     val = s["evals"] * args.steps / t / 1e9
-    sample = (f"rows [0,{s['nrows']}) x {s['cols']} cols of {args.workload} x {s['n']} points x {s['E']} exponent(s), "
+    sample = (f"rows [{s['row0']},{s['row0'] + s['nrows']}) x {s['cols']} cols of {args.workload} x {s['n']} points x {s['E']} exponent(s), "
               f"ChunkSolve semantics (1-row chunks over a {s['threads']}-thread pool), oracle port of the Go algorithm")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 0, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": _workload_name(args.workload, 1), "sample": sample},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": _workload_name(args, 1), "sample": sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": s["threads"], "kind": "port", "sample": sample,
                          "serial": s["run_serial"]()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -121,17 +154,26 @@ def reference_arm(args):
     return 0
 
 
-def _workload_name(name, world):
+def _workload_name(args, world):
     from v2r_b200 import workloads
-    s = workloads.SPECS[name]
+    s = workloads.SPECS[args.workload]
     exps = []
     e = s["es"]
     while e < s["ee"]:
         exps.append(e)
         e += s["ei"]
-    band = f"{s['cells']}x{s['cells']}"
-    grid = band if world == 1 else f"{s['cells'] * world}x{s['cells']} ({world} row bands of {band})"
-    return f"{name}: {s['n']} {s['kind']} points -> {grid} grid, p={exps if len(exps) > 1 else exps[0]}"
+    cells = s["cells"]
+    jr0, jnr = job_rows(args, cells)
+    if args.scaling == "weak":
+        grid = f"{cells}x{cells}" if world == 1 else f"{cells * world}x{cells} ({world} row bands of {cells}x{cells})"
+    elif (jr0, jnr) == (0, cells):
+        grid = f"{cells}x{cells}"
+    else:
+        grid = f"slab rows [{jr0},{jr0 + jnr}) of the {cells}x{cells} grid ({jnr}x{cells} cells)"
+    name = f"{args.workload}: {s['n']} {s['kind']} points -> {grid}, p={exps if len(exps) > 1 else exps[0]}"
+    if args.exps:
+        name += f" [exps overridden: {args.exps}]"
+    return name
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -201,14 +243,16 @@ def ours(args):
     L = _lib.load()
     prec = _lib.FP64 if args.precision == "fp64" else _lib.FP32
 
-    # ---- workload: every rank keeps one workload-sized row band (weak scaling) ----------------
+    # ---- workload ---------------------------------------------------------------------------------
     from v2r_b200.distributed import shard_rows
     x, y, w, xi, yi, exps = workloads.make(args.workload, scale_rows=world if args.scaling == "weak" else 1)
     if args.exps:
         exps = np.array([float(v) for v in args.exps.split(",")])
     ps = V.MakeCoordSpace(x, y, w, xi, yi)
     grid = make_grid(xi, yi)
-    row0, band = shard_rows(grid.rows, world, rank)      # contiguous row band of this rank
+    jr0, jnr = job_rows(args, grid.rows)                 # the job: rows [jr0, jr0 + jnr) of the grid
+    b0, band = shard_rows(jnr, world, rank)              # contiguous row band of this rank inside the job
+    row0 = jr0 + b0
     nrows = band if args.band_rows <= 0 else min(args.band_rows, band)
     n, E = len(ps), len(exps)
 
@@ -219,12 +263,11 @@ def ours(args):
     else:
         dx, dy, dw = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (ps.x, ps.y, ps.w))
         dkr, dkc = (torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev) for a in (ps.key_r, ps.key_c))
-    dout = torch.empty((E, nrows, grid.cols), dtype=torch.float64, device=dev)
+    dout = torch.empty((E, max(nrows, 1), grid.cols), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     exps_c = np.ascontiguousarray(exps, dtype=np.float64)
 
     def step():
-        nonlocal nrows
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(L.v2r_idw_launch_rows(local, C.c_void_p(stream), C.c_void_p(dx.data_ptr()), C.c_void_p(dy.data_ptr()),
                                          C.c_void_p(dw.data_ptr()), C.c_void_p(dkr.data_ptr()), C.c_void_p(dkc.data_ptr()), n,
@@ -236,15 +279,9 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up: full steps for the default workload; for the minutes-long ones (c3-c5) 512-row bands are
-    # enough to bring clocks, caches and the instruction cache to steady state
-    full_nrows = nrows
-    if args.workload != "c2":
-        nrows = min(nrows, 512 if n * E < 3_000_000 else 64)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3)):    # full steps: same launch as the timed ones
         step()
         flush.zero_()
-    nrows = full_nrows
     barrier()
     clocks = Clocks(local)
     if rank == 0:
@@ -273,17 +310,15 @@ def ours(args):
     pair_evals_step = float(tot_rows.item()) * grid.cols * n          # all ranks
     value = pair_evals_step * args.steps / (ms_total * 1e-3) / 1e9
 
-    # sanity: the band is finite and exact-hit cells carry their weights (cheap, device side)
-    assert bool(torch.isfinite(dout).all().item()), "non-finite raster in the bench band"
-
-    # ---- e2e through the C ABI with host buffers ------------------------------------------------
-    e2e = None
+    # ---- e2e through the C ABI with host buffers, and the parity block on its raster -------------------
+    e2e = parity = None
     if not args.no_e2e:
         def host_barrier():
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier(group=cpu_group)
-        e2e = run_e2e(args, V, L, ps, grid, exps_c, prec, world, rank, local, host_barrier, band)
+        e2e, parity = run_e2e(args, V, L, ps, xi, yi, grid, exps_c, prec, world, rank, local, host_barrier, jr0, jnr,
+                              dout if (world == 1 and args.band_rows <= 0) else None)
 
     # ---- roofline + peaks + cpu baseline (rank 0) --------------------------------------------------
     if rank == 0:
@@ -292,51 +327,52 @@ def ours(args):
         buf = C.create_string_buffer(512)
         ops = C.c_double()
         _lib.check(L.v2r_idw_describe(C.c_void_p(exps_c.ctypes.data), E, prec, buf, 512, C.byref(ops)))
-        A = ALGO_SLOTS[args.workload]
+        kernel = buf.value.decode()
+        A = None if args.exps else ALGO_SLOTS[args.workload]     # an overridden sweep has no SURVEY figure
         per_gpu_pairs_s = value * 1e9 / world
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        traffic = None
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(f"{args.workload}/{args.precision}")
-            except Exception:
-                traffic = None
+        traffic = lookup_traffic(kernel, nrows, int(grid.cols), n)
         peaks = {"dfma": dfma.value, "mufu_rcp64h": m64.value, "mufu_rcp_f32": m32.value, "ffma": ffma.value}
         for key, which in (("dfma_3src", 4), ("dadd", 5)):   # the operand forms the kernels actually issue
             v = C.c_double()
             _lib.check(L.v2r_idw_measure_peak(local, 60.0, which, C.byref(v)))
             peaks[key] = v.value
         if prec == _lib.FP64:
-            # FP64-pipe roofline: algorithmic slots per pair x 2 flop, against the DFMA issue rate
-            achieved_tflops = per_gpu_pairs_s * 2 * A / 1e12
+            # FP64-pipe roofline: algorithmic slots per pair x 2 flop, against the DFMA issue rate.
+            # `frac` can read above 1 because the paired-reciprocal kernel issues fewer slots than the algorithmic
+            # count; `fp64_pipe_busy_model` (issued slots / peak) is the utilisation of the pipe itself.
+            achieved_tflops = per_gpu_pairs_s * 2 * A / 1e12 if A else None
             peak_tflops = 2 * dfma.value / 1e3
             roofline = {
                 "bound": "fp64-pipe", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved_tflops / peak_tflops if peak_tflops else None, "traffic": traffic,
+                "frac": achieved_tflops / peak_tflops if (A and peak_tflops) else None, "traffic": traffic,
                 "peak_source": "in-run DFMA issue-rate microbenchmark (MEASURED_PEAKS.json has no FP64 entry)",
-                "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP64_TFLOPS,
+                "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP64_TFLOPS if A else None,
                 "algorithmic_fp64_slots_per_pair": A, "issued_fp64_slots_per_pair_model": ops.value,
                 "fp64_pipe_busy_model": per_gpu_pairs_s * ops.value / (dfma.value * 1e9) if dfma.value else None,
                 "frac_of_3src_dfma_rate_at_issued_slots": per_gpu_pairs_s * ops.value / (peaks["dfma_3src"] * 1e9) if peaks.get("dfma_3src") else None,
-                "kernel": buf.value.decode(), "ms_per_launch": ms_total / args.steps, "measured_peaks_ginst_s": peaks,
+                "kernel": kernel, "ms_per_launch": ms_total / args.steps, "measured_peaks_ginst_s": peaks,
             }
         else:
-            # FP32 path: 4 FP32 slots + 1 MUFU.RCP per pair => MUFU-bound; flops counted as 2 x 4
-            achieved_tflops = per_gpu_pairs_s * 8 / 1e12
-            peak_tflops = m32.value * 8 / 1e3
+            # FP32 path: the packed p = 2 kernel occupies 5.75 FP32-pipe lane slots per pair (184 per 2 points x 16 cells:
+            # 92 two-wide instructions); the bound is the FP32 pipe (FFMA rate), MUFU needs half a
+            # reciprocal per pair
+            fp32_slots = 5.75
+            achieved_tflops = per_gpu_pairs_s * fp32_slots / 1e12
+            peak_tflops = ffma.value / 1e3
             roofline = {
-                "bound": "fp32 fma+mufu (MUFU-bound at 1 reciprocal per pair)", "achieved": achieved_tflops, "peak": peak_tflops,
-                "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops if peak_tflops else None, "traffic": traffic,
-                "peak_source": "in-run MUFU.RCP issue-rate microbenchmark; the paired-reciprocal kernel needs half a MUFU per pair, "
-                               "so its own bound is the FP32 FMA pipe", "peak_nominal": 4.65 * 8,
-                "kernel": buf.value.decode(), "ms_per_launch": ms_total / args.steps, "measured_peaks_ginst_s": peaks,
+                "bound": "fp32 pipe (packed FFMA2/FADD2/FMUL2 issue at half the FFMA rate: flop slots per pair x pair rate vs FFMA rate)",
+                "achieved": achieved_tflops, "peak": peak_tflops, "unit": "T FP32 slots/s",
+                "frac": achieved_tflops / peak_tflops if (peak_tflops and not args.exps) else None, "traffic": traffic,
+                "peak_source": "in-run FFMA issue-rate microbenchmark", "fp32_slots_per_pair_model": fp32_slots,
+                "mufu_frac": per_gpu_pairs_s * 0.5 / (m32.value * 1e9) if m32.value else None,
+                "kernel": kernel, "ms_per_launch": ms_total / args.steps, "measured_peaks_ginst_s": peaks,
             }
         cpu = None
         if not args.no_cpu_baseline:
-            s = cpu_sample(args.workload, args.cpu_seconds)
+            s = cpu_sample(args, args.cpu_seconds)
             tc = s["run"]()
             cpu = {"value": s["evals"] / tc / 1e9, "unit": UNIT, "cores": s["threads"], "kind": "port",
-                   "sample": f"rows [0,{s['nrows']}) x {s['cols']} cols x {s['n']} points x {s['E']} exponent(s) of {args.workload}, "
+                   "sample": f"rows [{s['row0']},{s['row0'] + s['nrows']}) x {s['cols']} cols x {s['n']} points x {s['E']} exponent(s) of {args.workload}, "
                              f"oracle port of ChunkSolve (1-row chunks), {tc:.1f} s",
                    "serial": s["run_serial"]()}
         line = {
@@ -344,12 +380,12 @@ def ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64" if prec == _lib.FP64 else "f32(tile)/f64(accumulate)",
             "data": "synthetic",
-            "config": {"workload": _workload_name(args.workload, world if args.scaling == "weak" else 1) + (f" [exps overridden: {args.exps}]" if args.exps else ""),
-                       "points_after_dedupe": n, "exponents": E,
-                       "rows_per_rank": nrows, "cols": int(grid.cols), "l2": "flushed between timed iterations (256 MiB memset); output band > L2",
+            "config": {"workload": _workload_name(args, world), "points_after_dedupe": n, "exponents": E,
+                       "job_rows": [jr0, jr0 + jnr], "rows_per_rank": nrows, "cols": int(grid.cols),
+                       "l2": "flushed between timed iterations (256 MiB memset); output band > L2",
                        "parallelism": f"row bands x{world}"},
             "pair_evals_per_step": pair_evals_step, "raster_evals_per_s_G": value * E,
-            "wall_s": t_wall, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+            "wall_s": t_wall, "clocks": clk, "e2e": e2e, "parity": parity, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
@@ -359,30 +395,43 @@ def ours(args):
     return 0
 
 
-def run_e2e(args, V, L, ps, grid, exps_c, prec, world, rank, local, barrier, band):
-    """The call a user of the library makes: v2r_idw_solve with host buffers.  At N > 1 rank 0 drives all
-    N GPUs through ONE context (v2r_idw_init(N): NCCL broadcast of the points, row bands, gather to
-    device 0, D2H) -- the shape the Go host uses; the other ranks idle at the barrier."""
-    import ctypes as C
+def lookup_traffic(kernel, nrows, cols, n):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of THIS launch shape
+    (profiles/traffic.json, written by scripts/ncu_traffic.py); null when no capture matches."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        for rec in json.load(open(path)).get("captures", []):
+            if rec.get("kernel") == kernel and [rec.get("rows"), rec.get("cols"), rec.get("points")] == [nrows, cols, n]:
+                return rec.get("dram_bytes")
+    except Exception:
+        pass
+    return None
+
+
+def run_e2e(args, V, L, ps, xi, yi, grid, exps_c, prec, world, rank, local, barrier, jr0, jnr, dev_raster):
+    """The call a user of the library makes: v2r_idw_solve_rows with host buffers.  At N > 1 rank 0 drives all
+    N GPUs through ONE context (v2r_idw_init(N): NCCL broadcast of the points, a row band per device, every device
+    copies its band into the pinned host raster) -- the shape the Go host uses; the other ranks idle at the barrier.
+    Returns (e2e, parity)."""
     from v2r_b200 import _lib
     n, E = len(ps), len(exps_c)
-    res = None
+    res = par = None
     barrier()
     if rank == 0:
         ctx = V.IdwContext(n_gpus=world) if world > 1 else V.IdwContext(device=local)
-        rows = grid.rows if args.band_rows <= 0 else min(args.band_rows * world, grid.rows)
-        rows = min(rows, grid.rows)
+        rows = jnr if args.band_rows <= 0 else min(args.band_rows * world, jnr)
         nbytes_out = E * rows * grid.cols * 8
         pin = C.c_void_p()
-        _lib.check(L.v2r_idw_alloc_pinned(nbytes_out, C.byref(pin)))
-        out = np.ctypeslib.as_array((C.c_double * (nbytes_out // 8)).from_address(pin.value))
+        _lib.check(L.v2r_idw_alloc_pinned(max(nbytes_out, 8), C.byref(pin)))
+        out = np.ctypeslib.as_array((C.c_double * max(nbytes_out // 8, 1)).from_address(pin.value))[:nbytes_out // 8]
         # pinned inputs, as a reader filling v2r_idw_alloc_pinned buffers would leave them
         pins = []
+
         def pinned_copy(a):
             p = C.c_void_p()
-            _lib.check(L.v2r_idw_alloc_pinned(a.nbytes, C.byref(p)))
+            _lib.check(L.v2r_idw_alloc_pinned(max(a.nbytes, 8), C.byref(p)))
             pins.append(p)
-            v = np.ctypeslib.as_array((C.c_byte * a.nbytes).from_address(p.value)).view(a.dtype)
+            v = np.ctypeslib.as_array((C.c_byte * max(a.nbytes, 8)).from_address(p.value))[:a.nbytes].view(a.dtype)
             v[:] = a
             return v
         hx, hy, hw = pinned_copy(ps.x), pinned_copy(ps.y), pinned_copy(ps.w)
@@ -390,21 +439,82 @@ def run_e2e(args, V, L, ps, grid, exps_c, prec, world, rank, local, barrier, ban
         hps = V.PointSet(hx, hy, hw, hkr, hkc)
         out3 = out.reshape(E, rows, grid.cols)
         times = []
-        for i in range(1 + max(1, args.e2e_steps)):
+        for _ in range(1 + max(1, args.e2e_steps)):
             t0 = time.perf_counter()
-            ctx.solve_rows(hps, grid, 0, rows, exps_c, prec, out=out3)
+            ctx.solve_rows(hps, grid, jr0, rows, exps_c, prec, out=out3)
             times.append(time.perf_counter() - t0)
         tm = ctx.last_timing()
         t = sum(times[1:]) / len(times[1:])
         res = {"value": float(rows) * grid.cols * n / t / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(n * 40),
                "d2h_bytes_per_step": int(nbytes_out), "ms_per_step": t * 1e3, "steps": len(times) - 1,
-               "call": f"v2r_idw_solve_rows via v2r_idw_init({world}) with pinned host buffers",
-               "breakdown_ms": tm, "finite": bool(np.isfinite(out3[:, ::max(1, rows // 64)]).all())}
+               "call": f"v2r_idw_solve_rows via v2r_idw_init({world}) with pinned host buffers (rows [{jr0},{jr0 + rows}))",
+               "breakdown_ms": tm, "kernel_share": tm["kernel_ms"] / (t * 1e3) if t > 0 else None}
+        if not args.no_parity:
+            par = parity_block(args, V, ctx, ps, xi, yi, grid, exps_c, prec, world, local, jr0, rows, out3, dev_raster)
         ctx.close()
         for p in pins + [pin]:
             L.v2r_idw_free_pinned(p)
     barrier()
-    return res
+    return res, par
+
+
+def parity_block(args, V, ctx, ps, xi, yi, grid, exps_c, prec, world, local, jr0, rows, out3, dev_raster):
+    """Correctness of the N-GPU e2e raster, inside the bench (rank 0):
+    (1) bit-equality with a 1-GPU solve of the same rows (at N = 1: with the device-resident raster of the timed steps,
+        i.e. context path vs v2r_idw_launch_rows); (2) >= parity_cells random cells + every exact-hit cell of the job
+    against the CPU oracle (FP64: 1e-12 on max(|z|, sum|w|h / sum h); FP32: 2e-5); (3) exact hits bit-equal."""
+    from oracle import oracle as O
+    from v2r_b200 import _lib
+    E = len(exps_c)
+    t0 = time.perf_counter()
+    if world > 1:
+        with V.IdwContext(device=local) as one:
+            ref1 = one.solve_rows(ps, grid, jr0, rows, exps_c, prec)
+        bit_equal = bool(np.array_equal(out3, ref1, equal_nan=True))
+        del ref1
+        how = "1-GPU v2r_idw_solve_rows of the same rows"
+    elif dev_raster is not None:
+        bit_equal = bool(np.array_equal(out3, dev_raster.cpu().numpy(), equal_nan=True))
+        how = "device-resident raster of the timed v2r_idw_launch_rows steps"
+    else:
+        bit_equal, how = None, "skipped (diagnostic band)"
+    oi = lambda i: O.Info(i.min, i.max, i.step)  # noqa: E731
+    ops = O.PointSet(ps.x, ps.y, ps.w, ps.key_r, ps.key_c)
+    oabs = O.PointSet(ps.x, ps.y, np.abs(ps.w), ps.key_r, ps.key_c)
+    rng = np.random.default_rng(20261020)
+    ncell = max(0, args.parity_cells)
+    rr = jr0 + rng.integers(0, max(rows, 1), ncell)
+    cc = rng.integers(0, max(grid.cols, 1), ncell)
+    # first and last row of the job and of every device band are always sampled
+    from v2r_b200.distributed import shard_rows
+    edges = sorted({jr0, jr0 + rows - 1} | {jr0 + shard_rows(rows, world, g)[0] for g in range(world)})
+    edges = [r for r in edges if jr0 <= r < jr0 + rows]
+    rr = np.concatenate([rr, np.repeat(edges, 4)]).astype(np.int64)
+    cc = np.concatenate([cc, rng.integers(0, max(grid.cols, 1), 4 * len(edges))]).astype(np.int64)
+    inb = (ps.key_r >= jr0) & (ps.key_r < jr0 + rows) & (ps.key_c >= 0) & (ps.key_c < grid.cols)
+    hits_ok = bool(all(np.array_equal(out3[e][ps.key_r[inb] - jr0, ps.key_c[inb]], ps.w[inb]) for e in range(E)))
+    rel = REL64 if prec == _lib.FP64 else REL32
+    worst, nan_ok = 0.0, True
+    if rows > 0 and grid.cols > 0:
+        for e, p in enumerate(exps_c):
+            ref = O.solve_cells(ops, oi(xi), oi(yi), float(p), rr, cc)
+            scale = O.solve_cells(oabs, oi(xi), oi(yi), float(p), rr, cc)
+            got = out3[e][rr - jr0, cc]
+            nan_ok &= bool(np.array_equal(np.isnan(got), np.isnan(ref)))
+            ok = ~np.isnan(ref)
+            if ok.any():
+                err = np.abs(got[ok] - ref[ok]) / np.maximum(np.maximum(np.abs(ref[ok]), scale[ok]), 1e-300)
+                worst = max(worst, float(np.nanmax(err)))
+    passed = bool(nan_ok and hits_ok and worst <= rel and bit_equal is not False)
+    par = {"cells": int(len(rr)) * E, "max_scaled_err": worst, "tolerance": rel, "nan_positions_equal": nan_ok,
+           "bit_equal_1gpu": bit_equal, "bit_equal_against": how, "exact_hits": int(inb.sum()), "exact_hits_bit_equal": hits_ok,
+           "oracle": "oracle/libidw_oracle.so solve_cells (CPU restatement of calculateIDW), scale = the same solve on |w|",
+           "seconds": time.perf_counter() - t0, "pass": passed}
+    if prec != _lib.FP64:
+        par["max_rel_err"] = worst     # the observed accuracy of the FP32 path (north_star: ~1e-5)
+    if not passed:
+        print(f"PARITY FAILED: {json.dumps(par)}", file=sys.stderr)
+    return par
 
 
 def main():

@@ -24,8 +24,10 @@
  *     all indices int64 (Go `int` on amd64).
  *   - Every function returns an int status (0 = V2R_IDW_OK).  The message of the last failure on
  *     the calling thread is available from v2r_idw_last_error().  Nothing aborts or throws.
- *   - The library never keeps a caller pointer after the call returns (cgo rule).  `out` buffers are
- *     caller-provided; pinned buffers from v2r_idw_alloc_pinned() make the copies asynchronous.
+ *   - The library never keeps a caller pointer after the call returns (cgo rule): _solve* return when
+ *     `out` is complete, _stream_begin returns when the point arrays have been read completely.  `out`
+ *     buffers are caller-provided; pinned buffers from v2r_idw_alloc_pinned() make the copies asynchronous
+ *     inside a call.
  *   - Callable from any OS thread (goroutines migrate): every call sets its device explicitly and
  *     a context serialises its own calls with an internal mutex.
  *   - Raster layout = the reference's flattenGrid (features/idw/idw_utils.go:33-42): row-major
@@ -46,7 +48,7 @@
 extern "C" {
 #endif
 
-#define V2R_IDW_ABI_VERSION 1
+#define V2R_IDW_ABI_VERSION 2
 
 /* status codes */
 #define V2R_IDW_OK        0
@@ -72,11 +74,16 @@ typedef struct v2r_idw_grid {
 /* ---- library / device ------------------------------------------------------------------ */
 int v2r_idw_abi_version(void);
 const char *v2r_idw_last_error(void);
+/* Message of the last failed call that took this context, kept with the context: safe to fetch from another OS
+ * thread than the one that made the failing call (a goroutine may migrate between two cgo calls). */
+const char *v2r_idw_ctx_last_error(v2r_idw_ctx *ctx);
 int v2r_idw_device_count(int *count);
 
 /* One process driving GPUs 0..n_gpus-1 (n_gpus in {1,2,4,8}): the shape the Go host needs.
- * n_gpus > 1 loads NCCL (ncclCommInitAll): points are broadcast from device 0, each device
- * computes a row band, bands are gathered to device 0 and copied out from there. */
+ * n_gpus > 1 loads NCCL (ncclCommInitAll): points are broadcast from device 0 and each device
+ * computes a row band.  The bands reach the caller's host raster either straight from every device
+ * (one PCIe link per GPU; taken when `out` is page-locked, e.g. from v2r_idw_alloc_pinned) or, for
+ * pageable `out` (or V2R_IDW_GATHER=nccl), by an NCCL gather to device 0 and one copy from there. */
 int v2r_idw_init(int n_gpus, v2r_idw_ctx **out);
 /* One context on one given device: for one-process-per-GPU hosts (torchrun, MPI). */
 int v2r_idw_init_device(int device, v2r_idw_ctx **out);
@@ -107,7 +114,8 @@ int v2r_idw_make_coord_space(int64_t n, const double *x, const double *y, const 
 /* ---- the hot path, host buffers in / host buffers out --------------------------------- */
 /* Whole grid, all exponents, one pass over the points.
  *   x,y,z,key_r,key_c : n de-duplicated points (host memory, pageable or pinned)
- *   exps, n_exps      : the sweep (1 <= n_exps <= 64); each raster is IDW with exponent exps[e]
+ *   exps, n_exps      : the sweep (1 <= n_exps <= 4096; runs as passes of <= 10 exponents); each raster is IDW
+ *                       with exponent exps[e]
  *   out               : n_exps * rows * cols float64, host memory                                  */
 int v2r_idw_solve(v2r_idw_ctx *ctx, const double *x, const double *y, const double *z,
                   const int64_t *key_r, const int64_t *key_c, int64_t n, const v2r_idw_grid *grid,

@@ -1,5 +1,5 @@
 // Host-side accuracy check of v2r_b200/csrc/idw_math.cuh (the table-driven log2/exp2 of the general class): compiled with nvcc as a
-// plain host program by tests/test_math_cpu.py.  Prints "max_abs_log2 max_rel_exp2 max_rel_pow bad_specials".
+// plain host program by tests/test_math_cpu.py.  Prints "max_abs_log2 max_rel_exp2 max_rel_pow max_rel_pow_fold bad_specials".
 #include <cmath>
 #include <cstdio>
 #include <random>
@@ -8,15 +8,13 @@
 using namespace v2r;
 
 int main() {
-    static LogEntry lg[kLogTab];
-    static double ex[kExpTab];
-    for (int i = 0; i < kLogTab; i++) build_log_entry(i, lg[i]);
-    for (int j = 0; j < kExpTab; j++) ex[j] = build_exp_entry(j);
-    auto flog2 = [&](double a) { return tab_log2(a, lg); };
-    auto fexp2 = [&](double t) { return tab_exp2_32(32.0 * t, ex); };
+    static GenTables gt;
+    build_gen_tables(gt);
+    auto flog2 = [&](double a) { return tab_log2_any(a, gt.lg); };
+    auto fexp2 = [&](double t) { return tab_exp2<EXP_ANY>(kExpScale * t, gt.ex); };
     std::mt19937_64 g(1);
     std::uniform_real_distribution<double> U(0, 1);
-    double maxl = 0, maxe = 0, maxh = 0;
+    double maxl = 0, maxe = 0, maxh = 0, maxf = 0;
     for (long i = 0; i < 2000000; i++) {
         double a = std::exp2(U(g) * 200 - 100) * (1 + U(g));  // squared distances over 60 decades
         double el = fabs((double)(flog2(a) - log2l((long double)a)));
@@ -27,33 +25,53 @@ int main() {
         if (re > maxe) maxe = re;
         double c = -(U(g) * 5);  // c = -p/2 for p in (0, 10)
         long double ht = powl((long double)a, (long double)c);
-        double rh = fabs((double)((tab_exp2_32((32.0 * c) * flog2(a), ex) - ht) / ht));
+        double rh = fabs((double)((tab_exp2<EXP_ANY>((kExpScale * c) * flog2(a), gt.ex) - ht) / ht));
         if (rh > maxh) maxh = rh;
     }
     int bad = 0;
+    // the folded single-exponent form of the safe passes: T = 512 c log2(d2) straight from the log's last FMA, with the
+    // table's log2_c and the series coefficients pre-multiplied by 512 c; single-factor scaling for |c| <= 0.995
+    for (double pexp : {1.7, 0.3, 0.30000000000000004, 1.99, 0.1, 1.1, 2.2, 3.3, 3.75}) {
+        const double cs = kExpScale * (-pexp / 2.0);
+        static GenTables ft;
+        ft = gt;
+        for (int i = 0; i < kLogTab; ++i) ft.lg[i].log2_c = cs * gt.lg[i].log2_c;
+        const double l0 = cs * kLg[0], l1 = cs * kLg[1], l2 = cs * kLg[2];
+        for (long i = 0; i < 400000; i++) {
+            double a = std::exp2(U(g) * 200 - 100) * (1 + U(g));
+            if (i % 5 == 0) a = std::exp2(U(g) * 2040 - 1020) * (1 + U(g));  // the whole normal range
+            const double T = log2_core(a, ft.lg, l0, l1, l2, cs);
+            const double h = pexp <= 1.99 ? tab_exp2<EXP_SINGLE>(T, ft.ex) : tab_exp2<EXP_BOUNDED>(T, ft.ex);
+            long double ht = powl((long double)a, (long double)(-pexp / 2.0));
+            if ((double)ht == 0.0 || std::isinf((double)ht)) { bad += !(h == (double)ht); continue; }
+            if ((double)ht < 1e-290) continue;   // through the subnormals: only the two-factor form reaches here
+            double rf = fabs((double)((h - ht) / ht));
+            if (rf > maxf) maxf = rf;
+            if (pexp <= 1.99) bad += !(h == tab_exp2<EXP_BOUNDED>(T, ft.ex));   // the integer add equals the two multiplies
+        }
+    }
     // saturating specials: log2(0) is a huge negative FINITE number, inf / NaN give NaN
     for (double a0 : {0.0, -0.0, 1e-320}) bad += !(flog2(a0) < -1e300 && std::isfinite(flog2(a0)));
     bad += !std::isnan(flog2(INFINITY)) + !std::isnan(flog2(NAN));
-    bad += !(fabs(flog2(1.0)) < 3e-16) + !(fabs(flog2(2.0) - 1.0) < 3e-16) + !(fabs(flog2(0.5) + 1.0) < 3e-16);
+    bad += !(fabs(flog2(1.0)) < 6e-15) + !(fabs(flog2(2.0) - 1.0) < 6e-15) + !(fabs(flog2(0.5) + 1.0) < 6e-15);   // the series' design error
     const double ts[] = {0, -0.0, 1, -1, 1022, 1023, 1024, 1100, -1021, -3000, 3000, 2039.5, -2039.5, 2040, -2040, 2047.9, 1e300, -1e300};
     for (double t : ts) bad += !(fexp2(t) == exp2(t));
-    bad += !(fabs(fexp2(1023.9) / exp2(1023.9) - 1) < 1e-15);
+    bad += !(fabs(fexp2(1023.9) / exp2(1023.9) - 1) < 4e-15);
     for (double t : {-1022.5, -1040.0, -1074.0, -1075.0}) bad += !(fabs(fexp2(t) - exp2(t)) <= 1e-323);   // through the subnormals
     bad += !std::isnan(fexp2(NAN));
     // the compositions the kernel relies on: d2 = 0 with p > 0 -> +inf, p < 0 -> 0, p == 0 -> exactly 1
     bad += !(fexp2(-0.85 * flog2(0.0)) == INFINITY) + !(fexp2(0.5 * flog2(0.0)) == 0.0) + !(fexp2(0.0 * flog2(0.0)) == 1.0);
     bad += !(fexp2(-0.0 * flog2(123.0)) == 1.0) + !std::isnan(fexp2(-0.85 * flog2(NAN)));
-    // the (0 < p <= 3.75) specialisation: zero / subnormal / inf / NaN are poisoned to NaN by one range test, the
-    // exp2 clamp is skipped; on positive normal inputs and |t| < 2040 it must agree bit for bit with the general form
-    for (double a0 : {0.0, -0.0, 1e-320, (double)INFINITY, (double)NAN, -1.0}) bad += !std::isnan(tab_log2<true>(a0, lg));
+    // safe forms agree bit for bit with the saturating ones on positive normal inputs and |t| < 2040
     for (int i = 0; i < 200000; i++) {
         double a = std::exp2(U(g) * 2040 - 1020) * (1 + U(g));
-        double L = tab_log2<true>(a, lg);
-        bad += !(L == tab_log2<false>(a, lg));
-        double T = -32.0 * 1.875 * U(g) * L;
-        bad += !(tab_exp2_32<true>(T, ex) == tab_exp2_32<false>(T, ex));
+        double L = tab_log2_safe(a, gt.lg);
+        bad += !(L == tab_log2_any(a, gt.lg));
+        double T = -kExpScale * 1.875 * U(g) * L;
+        bad += !(tab_exp2<EXP_BOUNDED>(T, gt.ex) == tab_exp2<EXP_ANY>(T, gt.ex));
     }
-    bad += !std::isnan(tab_exp2_32<true>(-27.2 * tab_log2<true>(0.0, lg), ex));
+    // +inf distance (a point at infinity): weight ~ 0 relative to any finite point, never NaN, in the safe forms
+    bad += !(tab_exp2<EXP_SINGLE>(kExpScale * -0.85 * tab_log2_safe(INFINITY, gt.lg), gt.ex) < 1e-250);
     // base powers of the rcp / rsqrt / root4 classes: a ~2^-20 seed (emulated on the host by truncating operand and
     // result to their high words, the documented behaviour of MUFU.RCP64H / RSQ64H) plus ONE cubic step must reach
     // a few ulp; worst-case seeds are covered by sampling mantissas whose low words are all ones
@@ -69,6 +87,6 @@ int main() {
     bad += !(max1 < 4e-16) + !(max12 < 6e-16) + !(max14 < 8e-16);
     bad += !std::isnan(pow_m1(0.0)) + !std::isnan(pow_m12(0.0)) + !std::isnan(pow_m14(0.0));   // d = 0 off-key -> NaN cell
     fprintf(stderr, "base powers: max rel err rcp %.2e rsqrt %.2e root4 %.2e\n", max1, max12, max14);
-    printf("%.3e %.3e %.3e %d\n", maxl, maxe, maxh, bad);
+    printf("%.3e %.3e %.3e %.3e %d\n", maxl, maxe, maxh, maxf, bad);
     return 0;
 }

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(L, name), f"{name} declared in include/v2r_idw.h but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes binding and header disagree"
-    assert L.v2r_idw_abi_version() == 1
+    assert L.v2r_idw_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

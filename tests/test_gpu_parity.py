@@ -225,7 +225,7 @@ def test_error_behaviour(ctx):
     with pytest.raises(_lib.IdwError):
         ctx.solve_rows(ps, grid, 4, 10, [2.0], out=np.empty((1, 10, 8)))   # rows outside the grid
     with pytest.raises(_lib.IdwError):
-        ctx.solve(ps, grid, np.ones(65))                                     # too many exponents
+        ctx.solve(ps, grid, np.ones(4097))                                   # too many exponents
     with pytest.raises(ValueError):
         V.FullSolve(ps, "out.png", xi, yi, "", 2.0, ctx=ctx)                # idw.go:19-25 suffix check
     with pytest.raises(_lib.IdwError):

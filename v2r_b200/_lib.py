@@ -33,6 +33,7 @@ _P = C.c_void_p
 SIGNATURES = {
     "v2r_idw_abi_version": (C.c_int, []),
     "v2r_idw_last_error": (C.c_char_p, []),
+    "v2r_idw_ctx_last_error": (C.c_char_p, [_P]),
     "v2r_idw_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "v2r_idw_init": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "v2r_idw_init_device": (C.c_int, [C.c_int, C.POINTER(_P)]),

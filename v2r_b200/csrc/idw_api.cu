@@ -105,11 +105,13 @@ struct DeviceState {
     size_t pts_cap = 0, pts_stride = 0;  // elements per array
     double *d_band[2] = {nullptr, nullptr};
     size_t band_cap[2] = {0, 0};  // doubles
-    cudaEvent_t k_start[2] = {nullptr, nullptr}, k_stop[2] = {nullptr, nullptr};
-    cudaEvent_t c_start = nullptr, c_stop = nullptr, up_start = nullptr, up_stop = nullptr;
+    cudaEvent_t k_stop[2] = {nullptr, nullptr};    // kernels of the round that used buffer b have finished
+    cudaEvent_t drained[2] = {nullptr, nullptr};   // buffer b has been copied out / sent: it may be overwritten
+    bool drained_valid[2] = {false, false};
+    cudaEvent_t k_first = nullptr, k_last = nullptr, c_first = nullptr, c_last = nullptr, up_start = nullptr, up_stop = nullptr;
+    bool k_any = false, c_any = false;
     ncclComm_t comm = nullptr;
     long long band_row0 = 0, band_rows = 0;  // rows owned in the current session
-    double kernel_ms = 0;
 };
 
 struct Session {
@@ -123,6 +125,7 @@ struct Session {
     long long slice_off = 0;  // rows of the current (round, device) band already delivered
     long long rounds = 0;
     long long cur_round = 0;
+    long long launched = 0;   // rounds whose kernels are queued
     int cur_dev = 0;
     long long n = 0;
 };
@@ -132,10 +135,12 @@ struct Session {
 struct v2r_idw_ctx {
     std::mutex mu;
     std::vector<v2r::DeviceState> dev;
-    double *d_gather = nullptr;  // on device 0: landing buffer for peer bands
-    size_t gather_cap = 0;
+    double *d_land[2] = {nullptr, nullptr};  // on device 0: landing buffers for peer bands (NCCL gather path)
+    size_t land_cap[2] = {0, 0};
+    int land_next = 0;
     v2r::Session ses;
     double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0;
+    char err[512] = "";
 };
 
 namespace v2r {
@@ -145,7 +150,7 @@ static void free_device_state(DeviceState &d) {
     if (d.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d.comm);
     for (void *p : {(void *)d.d_pts, (void *)d.d_band[0], (void *)d.d_band[1]})
         if (p) cudaFree(p);
-    for (cudaEvent_t e : {d.k_start[0], d.k_start[1], d.k_stop[0], d.k_stop[1], d.c_start, d.c_stop, d.up_start, d.up_stop})
+    for (cudaEvent_t e : {d.k_stop[0], d.k_stop[1], d.drained[0], d.drained[1], d.k_first, d.k_last, d.c_first, d.c_last, d.up_start, d.up_stop})
         if (e) cudaEventDestroy(e);
     if (d.compute) cudaStreamDestroy(d.compute);
     if (d.copy) cudaStreamDestroy(d.copy);
@@ -157,13 +162,10 @@ static int init_device_state(DeviceState &d, int device) {
     CUDA_TRY(cudaStreamCreateWithFlags(&d.compute, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
-        CUDA_TRY(cudaEventCreate(&d.k_start[i]));
-        CUDA_TRY(cudaEventCreate(&d.k_stop[i]));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.k_stop[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.drained[i], cudaEventDisableTiming));
     }
-    CUDA_TRY(cudaEventCreate(&d.c_start));
-    CUDA_TRY(cudaEventCreate(&d.c_stop));
-    CUDA_TRY(cudaEventCreate(&d.up_start));
-    CUDA_TRY(cudaEventCreate(&d.up_stop));
+    for (cudaEvent_t *e : {&d.k_first, &d.k_last, &d.c_first, &d.c_last, &d.up_start, &d.up_stop}) CUDA_TRY(cudaEventCreate(e));
     return V2R_IDW_OK;
 }
 
@@ -247,6 +249,7 @@ static int ensure_points(DeviceState &d, size_t n) {
 
 // Upload the points to device 0 and replicate them to every other device with ONE NCCL broadcast over NVLink
 // (north_star: "the point set is replicated with one NCCL broadcast"): 5 * stride * 8 bytes, c4: 39 MB.
+// Returns only after the host arrays have been read completely (include/v2r_idw.h: no caller pointer is kept).
 static int upload_points(v2r_idw_ctx *ctx, const double *x, const double *y, const double *z, const int64_t *kr,
                          const int64_t *kc, long long n) {
     for (auto &d : ctx->dev) {
@@ -263,6 +266,8 @@ static int upload_points(v2r_idw_ctx *ctx, const double *x, const double *y, con
         CUDA_TRY(cudaMemcpyAsync(d0.d_kr, kr, n * 8, cudaMemcpyHostToDevice, d0.compute));
         CUDA_TRY(cudaMemcpyAsync(d0.d_kc, kc, n * 8, cudaMemcpyHostToDevice, d0.compute));
     }
+    cudaEvent_t h2d_done = d0.k_last;  // free at this point of a session; re-recorded by the first kernel round
+    CUDA_TRY(cudaEventRecord(h2d_done, d0.compute));
     if (ctx->dev.size() > 1 && n > 0) {
         NCCL_TRY(g_nccl.GroupStart());  // one collective; the group only spans this process's communicators
         for (auto &d : ctx->dev)
@@ -271,6 +276,7 @@ static int upload_points(v2r_idw_ctx *ctx, const double *x, const double *y, con
     }
     CUDA_TRY(cudaSetDevice(d0.device));
     CUDA_TRY(cudaEventRecord(d0.up_stop, d0.compute));
+    CUDA_TRY(cudaEventSynchronize(h2d_done));  // pinned host arrays make the copies truly asynchronous: wait for the DMA
     return V2R_IDW_OK;
 }
 
@@ -284,6 +290,8 @@ static void sub_band(const Session &s, const DeviceState &d, long long k, long l
     *nr = e > a ? e - a : 0;
 }
 
+// Queues the kernels of round k on every device.  Buffer k & 1 is reused every second round: the compute stream
+// waits (on the device, not the host) until the previous contents have been copied out.
 static int launch_round(v2r_idw_ctx *ctx, long long k) {
     Session &s = ctx->ses;
     const int buf = (int)(k & 1);
@@ -292,16 +300,29 @@ static int launch_round(v2r_idw_ctx *ctx, long long k) {
         sub_band(s, d, k, &r0, &nr);
         if (nr <= 0) continue;
         CUDA_TRY(cudaSetDevice(d.device));
-        CUDA_TRY(cudaEventRecord(d.k_start[buf], d.compute));
+        if (d.drained_valid[buf]) CUDA_TRY(cudaStreamWaitEvent(d.compute, d.drained[buf], 0));
+        if (!d.k_any) { CUDA_TRY(cudaEventRecord(d.k_first, d.compute)); d.k_any = true; }
         int rc;
         if (s.precision == V2R_IDW_FP32)
-            rc = launch_rows_fp32(d.compute, d.d_x, d.d_y, d.d_z, d.d_kr, d.d_kc, s.n, s.grid, r0, nr, s.exps.data(), (int)s.exps.size(), d.d_band[buf]);
+            rc = launch_rows_fp32(d.device, d.compute, d.d_x, d.d_y, d.d_z, d.d_kr, d.d_kc, s.n, s.grid, r0, nr, s.exps.data(), (int)s.exps.size(), d.d_band[buf]);
         else
-            rc = launch_rows_fp64(d.compute, d.d_x, d.d_y, d.d_z, d.d_kr, d.d_kc, s.n, s.grid, r0, nr, s.exps.data(), (int)s.exps.size(), d.d_band[buf]);
+            rc = launch_rows_fp64(d.device, d.compute, d.d_x, d.d_y, d.d_z, d.d_kr, d.d_kc, s.n, s.grid, r0, nr, s.exps.data(), (int)s.exps.size(), d.d_band[buf]);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(d.k_stop[buf], d.compute));
+        CUDA_TRY(cudaEventRecord(d.k_last, d.compute));
     }
+    s.launched = k + 1;
     return V2R_IDW_OK;
+}
+
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+static bool force_nccl_gather() {
+    static const bool v = getenv("V2R_IDW_GATHER") && !strcmp(getenv("V2R_IDW_GATHER"), "nccl");
+    return v;
 }
 
 static int begin_session(v2r_idw_ctx *ctx, const double *x, const double *y, const double *z, const int64_t *kr,
@@ -324,6 +345,7 @@ static int begin_session(v2r_idw_ctx *ctx, const double *x, const double *y, con
     s.precision = precision;
     s.n = n;
     ctx->h2d_ms = ctx->kernel_ms = ctx->d2h_ms = 0;
+    ctx->land_next = 0;
 
     const long long G = (long long)ctx->dev.size();
     // contiguous row band per device, multiple of 32 rows so CTA tiles stay whole
@@ -334,17 +356,22 @@ static int begin_session(v2r_idw_ctx *ctx, const double *x, const double *y, con
         long long a = std::min(row0 + g * per, row0 + nrows), e = std::min(a + per, row0 + nrows);
         d.band_row0 = a;
         d.band_rows = e - a;
-        d.kernel_ms = 0;
+        d.k_any = d.c_any = false;
+        d.drained_valid[0] = d.drained_valid[1] = false;
     }
-    // Launch granule (rows per device per round): at most ~1 GiB of output, and -- when the caller asks for
-    // small bands (the reference's default chunk is 200 rows) -- a multiple of the requested height that still
-    // gives the kernel >= ~16 waves of CTAs, so the WRITE granule of ChunkSolve does not starve the GPU.
-    const long long row_bytes = std::max<long long>(1, grid->cols) * 8 * n_exps;
+    // Launch granule (rows per device per round).  Every device's band is cut into up to 8 rounds of at least
+    // ~2 M cells and at most ~1 GiB of output, so the copy-out of round k overlaps the kernels of round k+1 and only
+    // the last round's copy is exposed; the kernels keep their efficiency on short bands because the last partial
+    // wave of a launch is shared out by point segments (idw_kernels.cuh).  When the caller asks for small bands
+    // (the reference's default chunk is 200 rows) the granule is a multiple of the requested height.
+    const long long cols1 = std::max<long long>(1, grid->cols);
+    const long long row_bytes = cols1 * 8 * n_exps;
     const long long cap_rows = std::max<long long>(32, ((1LL << 30) / row_bytes) / 32 * 32);
-    long long sub = cap_rows;
+    const long long min_rows = std::max<long long>(32, ceil_div(ceil_div(1LL << 21, cols1), 32) * 32);
+    long long sub = std::max(min_rows, ceil_div(ceil_div(per, 8), 32) * 32);
+    sub = std::min(sub, cap_rows);
     if (band_rows > 0) {
-        const long long want_rows = ceil_div(10000000LL, std::max<long long>(1, grid->cols));  // ~1e7 cells per launch
-        const long long k = std::max<long long>(1, std::min(ceil_div(want_rows, band_rows), std::max<long long>(1, cap_rows / band_rows)));
+        const long long k = std::max<long long>(1, std::min(ceil_div(sub, band_rows), std::max<long long>(1, cap_rows / band_rows)));
         sub = band_rows * k;
     }
     sub = std::min(sub, std::max<long long>(per, 1));
@@ -353,15 +380,11 @@ static int begin_session(v2r_idw_ctx *ctx, const double *x, const double *y, con
     s.slice_off = 0;
     s.rounds = per > 0 ? ceil_div(per, s.sub_rows) : 0;
 
-    const size_t band_doubles = (size_t)s.sub_rows * (size_t)std::max<long long>(grid->cols, 1) * (size_t)n_exps;
+    const size_t band_doubles = (size_t)s.sub_rows * (size_t)cols1 * (size_t)n_exps;
     for (auto &d : ctx->dev) {
         CUDA_TRY(cudaSetDevice(d.device));
         for (int i = 0; i < 2; ++i)
             if ((rc = ensure(d.d_band[i], d.band_cap[i], band_doubles))) return rc;
-    }
-    if (G > 1) {
-        CUDA_TRY(cudaSetDevice(ctx->dev[0].device));
-        if ((rc = ensure(ctx->d_gather, ctx->gather_cap, band_doubles))) return rc;
     }
     if ((rc = upload_points(ctx, x, y, z, kr, kc, n))) return rc;
     if (s.rounds > 0 && nrows > 0 && grid->cols > 0)
@@ -370,13 +393,87 @@ static int begin_session(v2r_idw_ctx *ctx, const double *x, const double *y, con
     return V2R_IDW_OK;
 }
 
-// Delivers the next slice (<= slice_rows rows) of the next (round, device) band.
-// out_base + e*plane_stride + row_off*cols receives exponent e (pack: planes of the slice's own height).
-static int next_band(v2r_idw_ctx *ctx, double *out_base, long long plane_stride, bool pack, long long *o_row0, long long *o_nrows) {
+// Queues the copy-out of rows [off, off + snr) of device g's band of round k (exponent planes at
+// dst + e * dst_stride).  Direct path: the device copies from its own band buffer (one PCIe link per GPU; used when
+// `dst` is page-locked, and always for device 0 and single-GPU contexts).  Gather path (north_star's shape, taken when
+// `dst` is pageable or V2R_IDW_GATHER=nccl): the band travels to device 0 over NVLink (ncclSend / ncclRecv into one
+// of two landing buffers) once per band, and is copied out from there.  Returns the stream the copy was queued on.
+static int queue_copy_out(v2r_idw_ctx *ctx, int g, long long k, long long off, long long snr, long long nr, double *dst,
+                          long long dst_stride, bool direct, bool first_slice, bool last_slice, cudaStream_t *queued_on) {
+    Session &s = ctx->ses;
+    DeviceState &d = ctx->dev[g];
+    DeviceState &d0 = ctx->dev[0];
+    const int buf = (int)(k & 1);
+    const int E = (int)s.exps.size();
+    const long long plane_src = nr * s.grid.cols, plane_dst = snr * s.grid.cols;
+    const double *src = d.d_band[buf];
+    DeviceState *cd = &d;  // device whose copy stream does the D2H
+    if (g != 0 && !direct) {
+        if (first_slice) {
+            const size_t need = (size_t)plane_src * E;
+            const int lb = ctx->land_next;
+            CUDA_TRY(cudaSetDevice(d0.device));
+            int rc = ensure(ctx->d_land[lb], ctx->land_cap[lb], need);  // (a reallocation synchronises the device: first use only)
+            if (rc) return rc;
+            CUDA_TRY(cudaSetDevice(d.device));
+            CUDA_TRY(cudaStreamWaitEvent(d.copy, d.k_stop[buf], 0));
+            NCCL_TRY(g_nccl.GroupStart());
+            NCCL_TRY(g_nccl.Send(d.d_band[buf], need, ncclDouble, 0, d.comm, d.copy));
+            NCCL_TRY(g_nccl.Recv(ctx->d_land[lb], need, ncclDouble, g, d0.comm, d0.copy));
+            NCCL_TRY(g_nccl.GroupEnd());
+            CUDA_TRY(cudaEventRecord(d.drained[buf], d.copy));  // the band has left this device
+            d.drained_valid[buf] = true;
+            ctx->land_next ^= 1;
+        }
+        src = ctx->d_land[ctx->land_next ^ 1];
+        cd = &d0;
+    }
+    CUDA_TRY(cudaSetDevice(cd->device));
+    if (cd == &d && first_slice) CUDA_TRY(cudaStreamWaitEvent(d.copy, d.k_stop[buf], 0));
+    if (!cd->c_any) { CUDA_TRY(cudaEventRecord(cd->c_first, cd->copy)); cd->c_any = true; }
+    for (int e = 0; e < E; ++e)
+        CUDA_TRY(cudaMemcpyAsync(dst + (long long)e * dst_stride, src + (long long)e * plane_src + off * s.grid.cols,
+                                 (size_t)plane_dst * 8, cudaMemcpyDeviceToHost, cd->copy));
+    CUDA_TRY(cudaEventRecord(cd->c_last, cd->copy));
+    if (cd == &d && last_slice) {
+        CUDA_TRY(cudaEventRecord(d.drained[buf], d.copy));
+        d.drained_valid[buf] = true;
+    }
+    *queued_on = cd->copy;
+    return V2R_IDW_OK;
+}
+
+// The whole row range into one host buffer: every round of every device is queued up front -- kernels, the
+// device-side waits for buffer reuse, the copies -- and the host only waits at the end (end_session).
+static int run_all(v2r_idw_ctx *ctx, double *out, long long plane_stride) {
+    Session &s = ctx->ses;
+    if (s.grid.cols == 0) return V2R_IDW_OK;
+    const int G = (int)ctx->dev.size();
+    const bool direct = G == 1 || (is_pinned(out) && !force_nccl_gather());
+    for (long long k = 0; k < s.rounds; ++k) {
+        if (k + 1 < s.rounds && s.launched < k + 2) {
+            int rc = launch_round(ctx, k + 1);  // waits on `drained` of round k-1, queued during iteration k-1
+            if (rc) return rc;
+        }
+        for (int g = 0; g < G; ++g) {
+            long long r0, nr;
+            sub_band(s, ctx->dev[g], k, &r0, &nr);
+            if (nr <= 0) continue;
+            cudaStream_t q;
+            int rc = queue_copy_out(ctx, g, k, 0, nr, nr, out + (r0 - s.row0) * s.grid.cols, plane_stride, direct, true, true, &q);
+            if (rc) return rc;
+        }
+    }
+    s.cur_round = s.rounds;
+    return V2R_IDW_OK;
+}
+
+// Delivers the next slice (<= slice_rows rows) of the next (round, device) band into out (planes of the slice's
+// own height, packed).
+static int next_band(v2r_idw_ctx *ctx, double *out, long long *o_row0, long long *o_nrows) {
     Session &s = ctx->ses;
     if (!s.active) return set_error(V2R_IDW_ESTATE, "no streaming session is open");
     const int G = (int)ctx->dev.size();
-    const int E = (int)s.exps.size();
     for (;;) {
         if (s.cur_round >= s.rounds || s.grid.cols == 0) {
             *o_row0 = s.row0 + s.nrows;
@@ -384,13 +481,7 @@ static int next_band(v2r_idw_ctx *ctx, double *out_base, long long plane_stride,
             return V2R_IDW_OK;
         }
         const bool band_start = s.slice_off == 0;
-        if (band_start && s.cur_dev == 0 && s.cur_round + 1 < s.rounds) {
-            int rc = launch_round(ctx, s.cur_round + 1);  // next round computes while this one is copied out
-            if (rc) return rc;
-        }
         DeviceState &d = ctx->dev[s.cur_dev];
-        DeviceState &d0 = ctx->dev[0];
-        const int buf = (int)(s.cur_round & 1);
         const int g = s.cur_dev;
         long long r0, nr;
         sub_band(s, d, s.cur_round, &r0, &nr);
@@ -398,43 +489,19 @@ static int next_band(v2r_idw_ctx *ctx, double *out_base, long long plane_stride,
             if (++s.cur_dev == G) { s.cur_dev = 0; ++s.cur_round; }
             continue;
         }
-        const long long plane_src = nr * s.grid.cols;
-        if (band_start) {
-            CUDA_TRY(cudaSetDevice(d.device));
-            CUDA_TRY(cudaStreamWaitEvent(d.copy, d.k_stop[buf], 0));
-            if (g != 0) {  // gather the whole band to rank 0 over NVLink (north_star); slices are copied out from there
-                NCCL_TRY(g_nccl.GroupStart());
-                NCCL_TRY(g_nccl.Send(d.d_band[buf], (size_t)plane_src * E, ncclDouble, 0, d.comm, d.copy));
-                NCCL_TRY(g_nccl.Recv(ctx->d_gather, (size_t)plane_src * E, ncclDouble, g, d0.comm, d0.copy));
-                NCCL_TRY(g_nccl.GroupEnd());
-            } else {
-                CUDA_TRY(cudaStreamSynchronize(d.copy));  // kernel of this band finished
-            }
-            float ms = 0;
-            if (g != 0) {
-                CUDA_TRY(cudaStreamSynchronize(d.copy));
-                CUDA_TRY(cudaSetDevice(d0.device));
-                CUDA_TRY(cudaStreamSynchronize(d0.copy));
-            }
-            if (cudaEventElapsedTime(&ms, d.k_start[buf], d.k_stop[buf]) == cudaSuccess) d.kernel_ms += ms;
-        }
-        const double *src = (g != 0) ? ctx->d_gather : d.d_band[buf];
         const long long sr0 = r0 + s.slice_off, snr = std::min(s.slice_rows, nr - s.slice_off);
-        CUDA_TRY(cudaSetDevice(d0.device));
-        CUDA_TRY(cudaEventRecord(d0.c_start, d0.copy));
-        const long long plane_dst = snr * s.grid.cols;
-        const long long stride = pack ? plane_dst : plane_stride;
-        const long long off = pack ? 0 : (sr0 - s.row0) * s.grid.cols;
-        for (int e = 0; e < E; ++e)
-            CUDA_TRY(cudaMemcpyAsync(out_base + (long long)e * stride + off, src + (long long)e * plane_src + s.slice_off * s.grid.cols,
-                                     (size_t)plane_dst * 8, cudaMemcpyDeviceToHost, d0.copy));
-        CUDA_TRY(cudaEventRecord(d0.c_stop, d0.copy));
-        CUDA_TRY(cudaStreamSynchronize(d0.copy));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, d0.c_start, d0.c_stop);
-        ctx->d2h_ms += ms;
+        const bool last_slice = s.slice_off + snr >= nr;
+        const bool direct = G == 1 || (is_pinned(out) && !force_nccl_gather());
+        cudaStream_t q;
+        int rc = queue_copy_out(ctx, g, s.cur_round, s.slice_off, snr, nr, out, snr * s.grid.cols, direct, band_start, last_slice, &q);
+        if (rc) return rc;
+        // the next round computes while this one is copied out: its kernels wait (on the device) for the buffers
+        // of round cur_round - 1, all of which were drained by earlier calls
+        if (band_start && g == 0 && s.cur_round + 1 < s.rounds && s.launched < s.cur_round + 2)
+            if ((rc = launch_round(ctx, s.cur_round + 1))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(q));
         s.slice_off += snr;
-        if (s.slice_off >= nr) {
+        if (last_slice) {
             s.slice_off = 0;
             if (++s.cur_dev == G) { s.cur_dev = 0; ++s.cur_round; }
         }
@@ -453,12 +520,25 @@ static int end_session(v2r_idw_ctx *ctx) {
         cudaError_t ce = cudaStreamSynchronize(d.compute);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(d.copy);
         if (ce != cudaSuccess && rc == V2R_IDW_OK) rc = set_error(V2R_IDW_ECUDA, "stream sync: %s", cudaGetErrorString(ce));
-        ctx->kernel_ms = std::max(ctx->kernel_ms, d.kernel_ms);
+        float ms = 0;
+        // span first kernel -> last kernel on this device (includes waits for a free band buffer, if any)
+        if (d.k_any && cudaEventElapsedTime(&ms, d.k_first, d.k_last) == cudaSuccess) ctx->kernel_ms = std::max(ctx->kernel_ms, (double)ms);
+        if (d.c_any && cudaEventElapsedTime(&ms, d.c_first, d.c_last) == cudaSuccess) ctx->d2h_ms = std::max(ctx->d2h_ms, (double)ms);
     }
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->dev[0].up_start, ctx->dev[0].up_stop) == cudaSuccess) ctx->h2d_ms = ms;
     cudaGetLastError();
     s.active = false;
+    return rc;
+}
+
+// keeps the message of a failed call with the context, so a caller that fetches it from another OS thread
+// (goroutines migrate between two cgo calls) still gets the right text
+static int remember(v2r_idw_ctx *ctx, int rc) {
+    if (rc != V2R_IDW_OK && ctx) {
+        strncpy(ctx->err, last_error(), sizeof ctx->err - 1);
+        ctx->err[sizeof ctx->err - 1] = 0;
+    }
     return rc;
 }
 
@@ -506,10 +586,9 @@ void v2r_idw_destroy(v2r_idw_ctx *ctx) {
     if (!ctx) return;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
-        if (ctx->d_gather) {
-            cudaSetDevice(ctx->dev[0].device);
-            cudaFree(ctx->d_gather);
-        }
+        cudaSetDevice(ctx->dev[0].device);
+        for (double *p : ctx->d_land)
+            if (p) cudaFree(p);
         for (auto &d : ctx->dev) free_device_state(d);
     }
     delete ctx;
@@ -624,18 +703,13 @@ int v2r_idw_solve_rows(v2r_idw_ctx *ctx, const double *x, const double *y, const
     if (!ctx) return set_error(V2R_IDW_EINVAL, "ctx is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (grid && nrows > 0 && grid->cols > 0 && !out) return set_error(V2R_IDW_EINVAL, "out is NULL");
-    return guarded([&] {
+    return remember(ctx, guarded([&] {
         int rc = begin_session(ctx, x, y, z, key_r, key_c, n, grid, row0, nrows, exps, n_exps, precision, 0);
         if (rc) return rc;
-        const long long plane = (long long)nrows * grid->cols;
-        for (;;) {
-            long long r0 = 0, nr = 0;
-            rc = next_band(ctx, out, plane, false, &r0, &nr);
-            if (rc || nr == 0) break;
-        }
+        rc = run_all(ctx, out, (long long)nrows * grid->cols);
         int rc2 = end_session(ctx);
         return rc ? rc : rc2;
-    });
+    }));
 }
 
 int v2r_idw_solve(v2r_idw_ctx *ctx, const double *x, const double *y, const double *z, const int64_t *key_r,
@@ -652,7 +726,7 @@ int v2r_idw_stream_begin(v2r_idw_ctx *ctx, const double *x, const double *y, con
     if (!grid) return set_error(V2R_IDW_EINVAL, "grid is NULL");
     if (band_rows < 0) return set_error(V2R_IDW_EINVAL, "band_rows < 0");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    return guarded([&] { return begin_session(ctx, x, y, z, key_r, key_c, n, grid, 0, grid->rows, exps, n_exps, precision, band_rows); });
+    return remember(ctx, guarded([&] { return begin_session(ctx, x, y, z, key_r, key_c, n, grid, 0, grid->rows, exps, n_exps, precision, band_rows); }));
 }
 
 int v2r_idw_stream_next(v2r_idw_ctx *ctx, double *out, int64_t *row0, int64_t *nrows) {
@@ -661,7 +735,7 @@ int v2r_idw_stream_next(v2r_idw_ctx *ctx, double *out, int64_t *row0, int64_t *n
     if (!out && ctx->ses.active && ctx->ses.cur_round < ctx->ses.rounds && ctx->ses.grid.cols > 0)
         return set_error(V2R_IDW_EINVAL, "out is NULL");
     long long r0 = 0, nr = 0;
-    int rc = guarded([&] { return next_band(ctx, out, 0, true, &r0, &nr); });
+    int rc = remember(ctx, guarded([&] { return next_band(ctx, out, &r0, &nr); }));
     *row0 = r0;
     *nrows = nr;
     return rc;
@@ -670,7 +744,13 @@ int v2r_idw_stream_next(v2r_idw_ctx *ctx, double *out, int64_t *row0, int64_t *n
 int v2r_idw_stream_end(v2r_idw_ctx *ctx) {
     if (!ctx) return set_error(V2R_IDW_EINVAL, "ctx is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    return end_session(ctx);
+    return remember(ctx, end_session(ctx));
+}
+
+const char *v2r_idw_ctx_last_error(v2r_idw_ctx *ctx) {
+    if (!ctx) return "";
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return ctx->err;
 }
 
 int v2r_idw_last_timing(v2r_idw_ctx *ctx, double *h2d_ms, double *kernel_ms, double *d2h_ms) {

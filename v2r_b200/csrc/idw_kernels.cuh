@@ -1,4 +1,5 @@
-// idw_kernels.cuh -- sm_100a kernels of the IDW gridding hot path (FP64 classes).
+// idw_kernels.cuh -- sm_100a kernels of the IDW gridding hot path (FP64 classes) and the tile driver they share with
+// the FP32 fast path (idw_kernels_fp32.cuh).
 //
 // Replaces the per-cell loop of the reference (features/idw/idw_utils.go:8-27 calculateIDW called
 // from features/idw/idw.go:34-40 and features/idw/idw_chunk.go:27-41):
@@ -9,13 +10,24 @@
 //   * a CTA owns a tile of (WARPS*CR) rows x (32*CC) columns; a thread owns a CR x CC register block
 //     (lanes run along columns so the raster stores coalesce);
 //   * the point stream (SoA x[], y[], w[]) is brought into shared memory by 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx), STAGES deep; every thread reads the same point at the
+//     (cp.async.bulk + mbarrier complete_tx), kStages deep; every thread reads the same point at the
 //     same time, i.e. shared-memory broadcasts;
 //   * per point and thread: CR squared dy and CC squared dx (reference: Pow(dx,2), Pow(dy,2),
 //     tools/utils.go:157 -- both exactly rounded products), then per pair ONE add d2 = dx2 + dy2
 //     (bit-identical to the reference's `total`), the power d2^(-p/2), one FMA and one ADD;
 //   * d^-p never goes through sqrt+pow: it is rcp / rsqrt / fourth-root seeds from MUFU.RCP64H /
 //     MUFU.RSQ64H refined by one cubic step in the FP64 pipe, or exp2(c*log2 d2) for general p.
+//
+// Work decomposition (the "tail" of a launch):
+//   * the points are cut into `segs` segments (a function of n only); a cell's sums are DEFINED as
+//     ((S_0 + S_1) + S_2) + ... over the per-segment sums, so the value of a cell does not depend on
+//     how the launch was cut into tiles, bands or devices (band / multi-GPU results are bit-identical);
+//   * CTAs [0, n_main) own one whole tile each: per-segment sums are folded into a running total that
+//     lives in shared memory ("stash"), touched once per segment;
+//   * the tiles that would form the last, partial wave are shared by the CTAs [n_main, n_main + n_tail):
+//     each takes a contiguous run of (tile, segment) units, writes per-segment partials to a global
+//     scratch area, and the CTA that delivers a tile's last segment adds them up in segment order and
+//     writes the cells.  The idle tail of a launch shrinks from one tile time to one segment time.
 //
 // No tensor cores: this is not a contraction (every pair needs its own reciprocal power).
 #pragma once
@@ -32,10 +44,17 @@ enum Mode : int {
     MODE_QRT = 2,  // all p are positive multiples of .5: base b = d2^(-1/4),  h = b^(2p)
     MODE_GEN = 3   // anything else (incl. p <= 0)      : h = exp2(c * log2 d2), c = -p/2 ; p == 0 -> h = 1
 };
+// MODE_GEN flavours (template parameter K0 of the kernel)
+enum GenKind : int {
+    GEN_ANY = 0,     // any exponents: saturating log2, clamped exp2 (p <= 0, large p, d2 == 0 handled in the loop)
+    GEN_SAFE = 1,    // all exponents in (0, 3.75]: no special cases in the loop (cells with d2 ~ 0 are poisoned afterwards)
+    GEN_SINGLE = 2   // all exponents in (0, 1.99]: additionally 2^n is one integer add (result always normal)
+};
 
 constexpr int kMaxE = 10;        // exponents per pass (register budget); longer sweeps run several passes
 constexpr int kTilePoints = 512; // points per shared-memory stage
 constexpr int kStages = 3;
+constexpr int kMaxSegs = 16;     // point segments per cell sum
 
 struct KParams {
     const double *x, *y, *w;  // device SoA, 16-byte aligned
@@ -46,7 +65,19 @@ struct KParams {
     double *out;              // E planes of nrows*cols
     long long plane;          // nrows * cols
     int k0, dk;               // integer power ladder: h_e = b^(k0 + e*dk) (runtime variant)
-    double cexp[kMaxE];       // MODE_GEN: 32 * (-p_e/2): the exponent multiplier, pre-scaled for tab_exp2_32
+    double cexp[kMaxE];       // MODE_GEN: 512 * (-p_e/2): the exponent multiplier, pre-scaled for tab_exp2
+    double lg_s[3];           // MODE_GEN, E == 1: cexp[0] * kLg[] (the multiplier folded into the log series)
+    // work decomposition (plan_grid, idw_launch.cu)
+    int tiles_x;              // CTA tiles per row of tiles
+    long long n_tiles;        // tiles_x * tile rows
+    long long n_main;         // CTAs [0, n_main) own one whole tile each
+    int n_tail;               // CTAs [n_main, n_main + n_tail) share tiles [n_main, n_tiles) by point segments
+    int segs;                 // point segments (function of n only)
+    int seg_tiles;            // point tiles per segment
+    double *scratch;          // tail partials: [tile - n_main][segment][accumulator][thread]
+    unsigned *counters;       // tail tiles: segments delivered so far (zero at launch, zero again at exit)
+    const GenTables *tables;  // MODE_GEN: table image in global memory (built once per device)
+    double inv_x_step, inv_y_step;  // tile guard of the paired kernels (approximate reciprocals are enough)
 };
 
 // ---------------------------------------------------------------------------- PTX helpers
@@ -83,6 +114,167 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                  : "memory");
 }
 
+// ---------------------------------------------------------------------------- shared memory layout
+// [ stages: kStages x {x, y, w} x kTilePoints doubles | mbarriers + flags (128 B) | body-specific area | stash ]
+constexpr int kStageBytes = kStages * 3 * kTilePoints * (int)sizeof(double);
+constexpr int kCtrlBytes = 128;
+struct Ctrl {
+    uint64_t full[kStages];
+    int finisher;     // tail tiles: this CTA delivered the last segment
+    int guard[2];     // paired kernels: point tile `it` is unsafe for pairing (slot it & 1)
+};
+static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block");
+
+__host__ __device__ constexpr int smem_bytes(int body_bytes, int nacc, int threads) {
+    return kStageBytes + kCtrlBytes + body_bytes + nacc * threads * (int)sizeof(double);
+}
+
+// ---------------------------------------------------------------------------- tile driver
+// Streams the point tiles of segments [s0, s1) of one cell tile through the TMA pipeline and hands them to Body:
+//   static constexpr int THREADS, NACC, BODY_BYTES;   double acc[NACC];
+//   void setup(p, tile_row, tile_col)          cell coordinates of this thread for tile (tile_row, tile_col)
+//   void points(p, sx, sy, sw, cnt, ctrl, it)  accumulate one point tile into acc[] (may __syncthreads: every thread calls it)
+//   void store(p)                              out = num / den for the thread's cells
+// WHOLE = all segments of the tile (the CTAs [0, n_main), one call each: the lean instantiation, whose loop state
+// is two counters -- the unrolled point loops of the bodies run at the register limit, and every extra live value
+// costs the scheduler operand-reuse slots); !WHOLE = a run of segments of a tail tile (the general instantiation).
+// `it` counts the point tiles this CTA has consumed: stage = it % kStages, mbarrier parity = (it / kStages) & 1.
+template <bool WHOLE, class Body>
+__device__ __forceinline__ unsigned run_piece(const KParams &p, Body &body, unsigned char *smem, int tile, int s0, int s1, unsigned it) {
+    constexpr int T = kTilePoints, S = kStages, THREADS = Body::THREADS, NACC = Body::NACC;
+    double(*sm)[3][T] = reinterpret_cast<double(*)[3][T]>(smem);
+    Ctrl *ctrl = reinterpret_cast<Ctrl *>(smem + kStageBytes);
+    double *stash = reinterpret_cast<double *>(smem + kStageBytes + kCtrlBytes + Body::BODY_BYTES);
+    const int tid = threadIdx.x;
+    const int K = p.segs;
+    const int ntp = (int)((p.n + T - 1) / T);  // point tiles
+    const int nfull = (int)(p.n / T);          // tiles fetched by TMA; a ragged last tile is loaded by the threads
+    const int pt_end = min(s1 * p.seg_tiles, ntp);
+    const int tma_end = min(pt_end, nfull);
+    const bool whole = WHOLE || (s0 == 0 && s1 == K);
+
+    auto issue = [&](int t, int st) {
+        mbar_expect_tx(&ctrl->full[st], 3u * T * (uint32_t)sizeof(double));
+        tma_load_1d(&sm[st][0][0], p.x + (long long)t * T, T * (uint32_t)sizeof(double), &ctrl->full[st]);
+        tma_load_1d(&sm[st][1][0], p.y + (long long)t * T, T * (uint32_t)sizeof(double), &ctrl->full[st]);
+        tma_load_1d(&sm[st][2][0], p.w + (long long)t * T, T * (uint32_t)sizeof(double), &ctrl->full[st]);
+    };
+
+    body.setup(p, tile / p.tiles_x, tile % p.tiles_x);
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) body.acc[i] = 0.0;
+    int pt = s0 * p.seg_tiles;
+    if (tid == 0)
+        for (int i = 0; i < S - 1; ++i)
+            if (pt + i < tma_end) issue(pt + i, (int)((it + i) % S));
+
+    for (int seg = s0; seg < s1; ++seg) {
+        const int seg_end = min((seg + 1) * p.seg_tiles, ntp);
+        for (; pt < seg_end; ++pt, ++it) {
+            const int st = (int)(it % S);
+            // stage (it-1)%S was released by the __syncthreads that ended the previous iteration
+            if (tid == 0 && pt + S - 1 < tma_end) issue(pt + S - 1, (int)((it + S - 1) % S));
+            int cnt = T;
+            if (pt >= nfull) {  // ragged last tile: ordinary loads, then complete the stage's phase by hand
+                const long long base = (long long)pt * T;
+                cnt = (int)(p.n - base);
+                for (int i = tid; i < cnt; i += THREADS) {
+                    sm[st][0][i] = p.x[base + i];
+                    sm[st][1][i] = p.y[base + i];
+                    sm[st][2][i] = p.w[base + i];
+                }
+                __syncthreads();
+                if (tid == 0) mbar_expect_tx(&ctrl->full[st], 0u);
+            }
+            mbar_wait(&ctrl->full[st], (it / S) & 1u);
+            body.points(p, sm[st][0], sm[st][1], sm[st][2], cnt, ctrl, it);
+            __syncthreads();
+        }
+        // end of segment `seg`: fold the segment sums into the running total (whole tiles: shared-memory stash,
+        // the last segment stays in registers) or hand them over (tail tiles: global scratch)
+        if (whole) {
+            if (seg + 1 < K) {
+                if (seg == 0) {
+#pragma unroll
+                    for (int i = 0; i < NACC; ++i) stash[i * THREADS + tid] = body.acc[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NACC; ++i) stash[i * THREADS + tid] += body.acc[i];
+                }
+#pragma unroll
+                for (int i = 0; i < NACC; ++i) body.acc[i] = 0.0;
+            }
+        } else {
+            double *dst = p.scratch + (((long long)(tile - (int)p.n_main) * K + seg) * NACC) * THREADS + tid;
+#pragma unroll
+            for (int i = 0; i < NACC; ++i) __stcg(dst + (long long)i * THREADS, body.acc[i]);
+#pragma unroll
+            for (int i = 0; i < NACC; ++i) body.acc[i] = 0.0;
+        }
+    }
+    if (whole) {
+        if (K > 1) {
+#pragma unroll
+            for (int i = 0; i < NACC; ++i) body.acc[i] = stash[i * THREADS + tid] + body.acc[i];
+        }
+        body.store(p);
+    } else {
+        const long long slot = tile - (int)p.n_main;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned old = atomicAdd(&p.counters[slot], (unsigned)(s1 - s0));
+            ctrl->finisher = (old + (unsigned)(s1 - s0) == (unsigned)K);
+        }
+        __syncthreads();
+        if (ctrl->finisher) {  // every segment of this tile is in scratch: add them in segment order
+            __threadfence();
+            const double *src = p.scratch + (slot * K * NACC) * THREADS + tid;
+#pragma unroll
+            for (int i = 0; i < NACC; ++i) {
+                double tot = __ldcg(src + (long long)i * THREADS);
+                for (int s = 1; s < K; ++s) tot += __ldcg(src + ((long long)s * NACC + i) * THREADS);
+                body.acc[i] = tot;
+            }
+            body.store(p);
+            if (tid == 0) p.counters[slot] = 0;  // leave the counters clean for the next launch
+        }
+        __syncthreads();
+    }
+    return it;
+}
+
+template <class Body>
+__device__ __forceinline__ void tile_driver(const KParams &p, Body &body, unsigned char *smem) {
+    Ctrl *ctrl = reinterpret_cast<Ctrl *>(smem + kStageBytes);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&ctrl->full[s], 1);
+        ctrl->finisher = 0;
+        ctrl->guard[0] = ctrl->guard[1] = 0;
+        mbar_fence_init();
+    }
+    __syncthreads();  // also publishes whatever Body's constructor wrote to its shared area
+    const int K = p.segs;
+    if ((long long)blockIdx.x < p.n_main) {
+        run_piece<true>(p, body, smem, (int)blockIdx.x, 0, K, 0u);
+    } else {
+        // tail CTA: a contiguous run of (tile, segment) units, unit = tile * K + segment
+        const long long j = (long long)blockIdx.x - p.n_main;
+        const long long U = (p.n_tiles - p.n_main) * K;
+        int u = (int)(p.n_main * K + j * U / p.n_tail);
+        const int u1 = (int)(p.n_main * K + (j + 1) * U / p.n_tail);
+        unsigned it = 0;
+        while (u < u1) {
+            const int tile = u / K, s0 = u - tile * K;
+            const int s1 = (u1 - u < K - s0) ? s0 + (u1 - u) : K;
+            it = run_piece<false>(p, body, smem, tile, s0, s1, it);
+            u += s1 - s0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- powers
 // b^K as a balanced product b^(K/2) * b^(K - K/2): depth log2 K instead of K.  In a sweep every exponent calls
 // this with its own K; the common sub-powers are merged by the compiler (pure FP multiplies of identical
 // operands), so consecutive powers 1..9 still cost 8 multiplies but the dependent chain is 4 deep, not 8.
@@ -124,25 +316,20 @@ __device__ __forceinline__ void static_powers(double b, double (&h)[E]) {
 }
 
 // h[e] = d2^(-p_e/2) for all exponents of the pass.
-// Shared-memory tables of the general class (2 KB + 256 B), built once per CTA.
-struct GenTables {
-    LogEntry lg[kLogTab];
-    double ex[kExpTab];
-};
-
 template <int MODE, int E, int K0, int DK>
 __device__ __forceinline__ void weights(double d2, const KParams &p, const GenTables *gt, double (&h)[E]) {
     if constexpr (MODE == MODE_GEN) {
-        // K0 == 1 marks a pass whose exponents all satisfy 0 < p <= 3.75 (decided on the host): d2 = 0 may then be
-        // poisoned to NaN straight away (the cell is NaN in the reference too) and |c * L| < 2040 needs no clamp.
-        constexpr bool SAFE = (K0 == 1);
-        const double L = tab_log2<SAFE>(d2, gt->lg);
+        constexpr int XM = K0 == GEN_SINGLE ? EXP_SINGLE : (K0 == GEN_SAFE ? EXP_BOUNDED : EXP_ANY);
+        if constexpr (E == 1 && K0 != GEN_ANY) {
+            // folded form: the CTA's log table and p.lg_s carry the factor 512 c, the log's last FMA delivers T
+            h[0] = tab_exp2<XM>(log2_core(d2, gt->lg, p.lg_s[0], p.lg_s[1], p.lg_s[2], p.cexp[0]), gt->ex);
+        } else {
+            // In the `any` form L is finite (saturating log2), so p == 0 gives 0 * L == 0 and exp2(0) == 1 exactly:
+            // Go's Pow(d, -0) == 1 even at d == 0 needs no special case; d == 0 with p > 0 -> +inf -> NaN cell,
+            // p < 0 -> 0.
+            const double L = (K0 == GEN_ANY) ? tab_log2_any(d2, gt->lg) : tab_log2_safe(d2, gt->lg);
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            // cexp holds 32 * (-p/2).  In the general form L is finite (saturating log2), so p == 0 gives 0 * L == 0
-            // and exp2(0) == 1 exactly: Go's Pow(d, -0) == 1 even at d == 0 needs no special case; d == 0 with
-            // p > 0 -> +inf -> NaN cell, p < 0 -> 0.
-            h[e] = tab_exp2_32<SAFE>(p.cexp[e] * L, gt->ex);
+            for (int e = 0; e < E; ++e) h[e] = tab_exp2<XM>(p.cexp[e] * L, gt->ex);
         }
     } else {
         double b = base_pow<MODE>(d2);
@@ -159,118 +346,82 @@ __device__ __forceinline__ void weights(double d2, const KParams &p, const GenTa
     }
 }
 
-// ---------------------------------------------------------------------------- main kernel
+// Tile guard of the paired kernels.  Pairing two points under one reciprocal needs the product of their squared
+// distances to stay a normal double for EVERY cell of the CTA tile.  A point is unsafe for the tile when some cell
+// is closer than `tiny` to it in both axes (or it coincides with a node: d2 == 0 must yield NaN through the
+// one-reciprocal code) or farther than `far` in either axis; NaN coordinates are unsafe too.  O(1) per point:
+// the nearest node column / row of the tile is found by rounding, its neighbours cover the rounding of the division.
+template <typename F>
+__device__ __forceinline__ bool pairing_unsafe(double x, double y, const KParams &p, long long c_lo, long long c_hi,
+                                               long long r_lo, long long r_hi, F tiny, F far) {
+    auto axis = [&](double v, double vmin, double step, double inv_step, long long lo, long long hi, double &dmin, double &dmax) {
+        const double q = rint((v - vmin) * inv_step);
+        long long k = (q >= (double)hi) ? hi : ((q <= (double)lo) ? lo : (long long)q);  // NaN -> lo
+        dmin = INFINITY;
+#pragma unroll
+        for (int d = -1; d <= 1; ++d) {
+            long long kk = k + d;
+            kk = kk < lo ? lo : (kk > hi ? hi : kk);
+            dmin = fmin(dmin, fabs(v - __dadd_rn(vmin, __dmul_rn((double)kk, step))));
+        }
+        dmax = fmax(fabs(v - __dadd_rn(vmin, __dmul_rn((double)lo, step))), fabs(v - __dadd_rn(vmin, __dmul_rn((double)hi, step))));
+    };
+    double xmin_d, xmax_d, ymin_d, ymax_d;
+    axis(x, p.x_min, p.x_step, p.inv_x_step, c_lo, c_hi, xmin_d, xmax_d);
+    axis(y, p.y_min, p.y_step, p.inv_y_step, r_lo, r_hi, ymin_d, ymax_d);
+    const bool safe = (xmin_d >= (double)tiny || ymin_d >= (double)tiny) && xmax_d <= (double)far && ymax_d <= (double)far;
+    return !safe;  // NaN anywhere -> comparisons false -> unsafe
+}
+
+// ---------------------------------------------------------------------------- FP64 body
 //
 // PAIRED (p == 2 only): two points share ONE reciprocal, 1/a + 1/b = (a+b)/(ab) and
 // w0/a + w1/b = (w0 b + w1 a)/(ab): 11 FP64 instructions per two pairs instead of 12, and half the MUFU
-// traffic.  Needs a*b to stay a normal double (squared distances in (1e-154, 1e154)).
-template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS, int MINB, int PAIRED = 0>
-__global__ void __launch_bounds__(THREADS, MINB) idw_fp64_kernel(const __grid_constant__ KParams p) {
-    static_assert(!PAIRED || (MODE == MODE_RCP && E == 1 && K0 == 1), "pairing is the p = 2 trick");
-    constexpr int UNR = PAIRED > 1 ? PAIRED : 1;  // PAIRED = unroll factor of the two-point loop
-    constexpr int WARPS = THREADS / 32;
-    constexpr int T = kTilePoints;
-    constexpr int S = kStages;
-    __shared__ __align__(128) double sm[S][3][T];
-    __shared__ __align__(8) uint64_t full[S];
-    const GenTables *gt = nullptr;
-    if constexpr (MODE == MODE_GEN) {  // visible to all threads after the __syncthreads that follows the mbarrier init
-        __shared__ __align__(16) GenTables gen_tables;
-        for (int i = threadIdx.x; i < kLogTab; i += THREADS) build_log_entry(i, gen_tables.lg[i]);
-        for (int j = threadIdx.x; j < kExpTab; j += THREADS) gen_tables.ex[j] = build_exp_entry(j);
-        gt = &gen_tables;
-    }
+// traffic.  Needs a*b to stay a normal double; point tiles for which that cannot be guaranteed on this CTA's cells
+// (pairing_unsafe) run through the one-reciprocal loop instead.
+template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS_, int PAIRED>
+struct Fp64Body {
+    static constexpr int THREADS = THREADS_;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int NACC = 2 * E * CR * CC;  // acc[((e*CR + a)*CC + b)*2 + {0: num, 1: den}]
+    static constexpr int BODY_BYTES = (MODE == MODE_GEN) ? (int)sizeof(GenTables) : 0;
+    static constexpr int UNR = PAIRED > 1 ? PAIRED : 1;
 
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const long long c_base = (long long)blockIdx.x * (32 * CC) + lane;
-    const long long r_base = p.row0 + ((long long)blockIdx.y * WARPS + warp) * CR;
-
-    // RCToPoint (tools/utils.go:78-82): px = xMin + float64(c)*xStep, multiply then add, unfused.
+    double acc[NACC];
     double cx[CC], cy[CR];
-#pragma unroll
-    for (int b = 0; b < CC; ++b) cx[b] = __dadd_rn(p.x_min, __dmul_rn((double)(c_base + 32 * b), p.x_step));
-#pragma unroll
-    for (int a = 0; a < CR; ++a) cy[a] = __dadd_rn(p.y_min, __dmul_rn((double)(r_base + a), p.y_step));
+    int tile_r, tile_c;         // tile indices of the CTA tile
+    const GenTables *gt;
 
-    double num[E][CR][CC], den[E][CR][CC];
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-#pragma unroll
-        for (int a = 0; a < CR; ++a)
-#pragma unroll
-            for (int b = 0; b < CC; ++b) { num[e][a][b] = 0.0; den[e][a][b] = 0.0; }
-
-    const long long ntiles = (p.n + T - 1) / T;
-    const long long nfull = p.n / T;  // tiles fetched by TMA; a ragged last tile is loaded by the threads
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    auto issue = [&](long long t) {
-        const int s = (int)(t % S);
-        mbar_expect_tx(&full[s], 3u * T * (uint32_t)sizeof(double));
-        tma_load_1d(&sm[s][0][0], p.x + t * T, T * (uint32_t)sizeof(double), &full[s]);
-        tma_load_1d(&sm[s][1][0], p.y + t * T, T * (uint32_t)sizeof(double), &full[s]);
-        tma_load_1d(&sm[s][2][0], p.w + t * T, T * (uint32_t)sizeof(double), &full[s]);
-    };
-    if (threadIdx.x == 0) {
-        for (long long t = 0; t < S - 1 && t < nfull; ++t) issue(t);
+    __device__ __forceinline__ Fp64Body(const KParams &p, unsigned char *smem) : gt(nullptr) {
+        if constexpr (MODE == MODE_GEN) {
+            // copy the table image global -> shared; single-exponent safe passes fold 512 c into log2_c
+            GenTables *t = reinterpret_cast<GenTables *>(smem + kStageBytes + kCtrlBytes);
+            constexpr bool FOLD = (E == 1 && K0 != GEN_ANY);
+            for (int i = threadIdx.x; i < kLogTab; i += THREADS) {
+                LogEntry e = p.tables->lg[i];
+                if constexpr (FOLD) e.log2_c = p.cexp[0] * e.log2_c;
+                t->lg[i] = e;
+            }
+            for (int j = threadIdx.x; j < kExpTab; j += THREADS) t->ex[j] = p.tables->ex[j];
+            gt = t;
+        }
     }
 
-    for (long long t = 0; t < ntiles; ++t) {
-        const int s = (int)(t % S);
-        int cnt = T;
-        // stage (t-1)%S was released by the __syncthreads that ended iteration t-1
-        if (threadIdx.x == 0 && t + S - 1 < nfull) issue(t + S - 1);
-        if (t < nfull) {
-            mbar_wait(&full[s], (uint32_t)((t / S) & 1));
-        } else {
-            cnt = (int)(p.n - t * T);
-            for (int i = threadIdx.x; i < cnt; i += THREADS) {
-                sm[s][0][i] = p.x[t * T + i];
-                sm[s][1][i] = p.y[t * T + i];
-                sm[s][2][i] = p.w[t * T + i];
-            }
-            __syncthreads();
-        }
-        const double *sx = sm[s][0], *sy = sm[s][1], *sw = sm[s][2];
-        int i = 0;
-        if constexpr (PAIRED) {
-#pragma unroll UNR
-            for (; i + 1 < cnt; i += 2) {
-                const double2 x = *reinterpret_cast<const double2 *>(sx + i);
-                const double2 y = *reinterpret_cast<const double2 *>(sy + i);
-                const double2 w = *reinterpret_cast<const double2 *>(sw + i);
-                double ax[CC], bx[CC], ay[CR], by[CR];
+    __device__ __forceinline__ long long row_base(const KParams &p) const { return p.row0 + (long long)tile_r * (WARPS * CR) + (threadIdx.x >> 5) * CR; }
+    __device__ __forceinline__ long long col_base() const { return (long long)tile_c * (32 * CC) + (threadIdx.x & 31); }
+
+    __device__ __forceinline__ void setup(const KParams &p, int tr, int tc) {
+        tile_r = tr;
+        tile_c = tc;
+        const long long c_base = col_base(), r_base = row_base(p);
+        // RCToPoint (tools/utils.go:78-82): px = xMin + float64(c)*xStep, multiply then add, unfused.
 #pragma unroll
-                for (int b = 0; b < CC; ++b) {
-                    double d0 = __dsub_rn(x.x, cx[b]), d1 = __dsub_rn(x.y, cx[b]);
-                    ax[b] = __dmul_rn(d0, d0);
-                    bx[b] = __dmul_rn(d1, d1);
-                }
+        for (int b = 0; b < CC; ++b) cx[b] = __dadd_rn(p.x_min, __dmul_rn((double)(c_base + 32 * b), p.x_step));
 #pragma unroll
-                for (int a = 0; a < CR; ++a) {
-                    double d0 = __dsub_rn(y.x, cy[a]), d1 = __dsub_rn(y.y, cy[a]);
-                    ay[a] = __dmul_rn(d0, d0);
-                    by[a] = __dmul_rn(d1, d1);
-                }
-#pragma unroll
-                for (int a = 0; a < CR; ++a)
-#pragma unroll
-                    for (int b = 0; b < CC; ++b) {
-                        const double A = __dadd_rn(ax[b], ay[a]), B = __dadd_rn(bx[b], by[a]);
-                        const double r = pow_m1(A * B);
-                        const double N = fma(w.x, B, w.y * A);
-                        num[0][a][b] = fma(N, r, num[0][a][b]);
-                        den[0][a][b] = fma(A + B, r, den[0][a][b]);
-                    }
-            }
-        }
+        for (int a = 0; a < CR; ++a) cy[a] = __dadd_rn(p.y_min, __dmul_rn((double)(r_base + a), p.y_step));
+    }
+
+    __device__ __forceinline__ void single_points(const KParams &p, const double *sx, const double *sy, const double *sw, int i, int cnt) {
 #pragma unroll 1
         for (; i < cnt; ++i) {
             const double x = sx[i], y = sy[i], w = sw[i];
@@ -289,28 +440,88 @@ __global__ void __launch_bounds__(THREADS, MINB) idw_fp64_kernel(const __grid_co
                     weights<MODE, E, K0, DK>(d2, p, gt, h);
 #pragma unroll
                     for (int e = 0; e < E; ++e) {
-                        num[e][a][b] = fma(w, h[e], num[e][a][b]);
-                        den[e][a][b] += h[e];
+                        double &num = acc[((e * CR + a) * CC + b) * 2], &den = acc[((e * CR + a) * CC + b) * 2 + 1];
+                        num = fma(w, h[e], num);
+                        den += h[e];
                     }
                 }
         }
-        __syncthreads();
     }
 
-    const long long row_end = p.row0 + p.nrows;
+    __device__ __forceinline__ void points(const KParams &p, const double *sx, const double *sy, const double *sw, int cnt,
+                                           Ctrl *ctrl, unsigned it) {
+        int i = 0;
+        if constexpr (PAIRED) {
+            static_assert(MODE == MODE_RCP && E == 1 && K0 == 1, "pairing is the p = 2 trick");
+            const int slot = it & 1;
+            bool unsafe = false;
+            const long long tc0 = (long long)tile_c * (32 * CC), tr0 = p.row0 + (long long)tile_r * (WARPS * CR);
+            for (int k = threadIdx.x; k < cnt; k += THREADS)
+                unsafe |= pairing_unsafe(sx[k], sy[k], p, tc0, tc0 + 32 * CC - 1, tr0, tr0 + WARPS * CR - 1, 0x1p-250, 0x1p+249);
+            if (unsafe) ctrl->guard[slot] = 1;
+            __syncthreads();
+            const bool paired_ok = !ctrl->guard[slot];
+            if (threadIdx.x == 0) ctrl->guard[slot ^ 1] = 0;  // nobody touches the other slot until the next tile
+            if (paired_ok) {
+#pragma unroll UNR
+                for (; i + 1 < cnt; i += 2) {
+                    const double2 x = *reinterpret_cast<const double2 *>(sx + i);
+                    const double2 y = *reinterpret_cast<const double2 *>(sy + i);
+                    const double2 w = *reinterpret_cast<const double2 *>(sw + i);
+                    double ax[CC], bx[CC], ay[CR], by[CR];
 #pragma unroll
-    for (int a = 0; a < CR; ++a) {
-        const long long r = r_base + a;
-        if (r >= row_end) continue;
+                    for (int b = 0; b < CC; ++b) {
+                        double d0 = __dsub_rn(x.x, cx[b]), d1 = __dsub_rn(x.y, cx[b]);
+                        ax[b] = __dmul_rn(d0, d0);
+                        bx[b] = __dmul_rn(d1, d1);
+                    }
 #pragma unroll
-        for (int b = 0; b < CC; ++b) {
-            const long long c = c_base + 32 * b;
-            if (c >= p.cols) continue;
+                    for (int a = 0; a < CR; ++a) {
+                        double d0 = __dsub_rn(y.x, cy[a]), d1 = __dsub_rn(y.y, cy[a]);
+                        ay[a] = __dmul_rn(d0, d0);
+                        by[a] = __dmul_rn(d1, d1);
+                    }
 #pragma unroll
-            for (int e = 0; e < E; ++e)
-                p.out[(long long)e * p.plane + (r - p.row0) * p.cols + c] = num[e][a][b] / den[e][a][b];
+                    for (int a = 0; a < CR; ++a)
+#pragma unroll
+                        for (int b = 0; b < CC; ++b) {
+                            const double A = __dadd_rn(ax[b], ay[a]), B = __dadd_rn(bx[b], by[a]);
+                            const double r = pow_m1(A * B);
+                            const double N = fma(w.x, B, w.y * A);
+                            double &num = acc[(a * CC + b) * 2], &den = acc[(a * CC + b) * 2 + 1];
+                            num = fma(N, r, num);
+                            den = fma(A + B, r, den);
+                        }
+                }
+            }
+        }
+        single_points(p, sx, sy, sw, i, cnt);
+    }
+
+    __device__ __forceinline__ void store(const KParams &p) {
+        const long long row_end = p.row0 + p.nrows, r_base = row_base(p), c_base = col_base();
+#pragma unroll
+        for (int a = 0; a < CR; ++a) {
+            const long long r = r_base + a;
+            if (r >= row_end) continue;
+#pragma unroll
+            for (int b = 0; b < CC; ++b) {
+                const long long c = c_base + 32 * b;
+                if (c >= p.cols) continue;
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    p.out[(long long)e * p.plane + (r - p.row0) * p.cols + c] =
+                        acc[((e * CR + a) * CC + b) * 2] / acc[((e * CR + a) * CC + b) * 2 + 1];
+            }
         }
     }
+};
+
+template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS, int MINB, int PAIRED = 0>
+__global__ void __launch_bounds__(THREADS, MINB) idw_fp64_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Fp64Body<MODE, E, CR, CC, K0, DK, THREADS, PAIRED> body(p, smem);
+    tile_driver(p, body, smem);
 }
 
 }  // namespace v2r

@@ -1,17 +1,28 @@
 // idw_kernels_fp32.cuh -- the optional FP32 fast path of the IDW kernels (precision = V2R_IDW_FP32).
 //
-// Same tiling and TMA point pipeline as the FP64 kernels; what changes:
-//   * coordinates become CTA-local: every staged FP64 tile is re-expressed relative to the centre of
-//     the CTA's cell tile (one FP64 subtract per point and CTA) and split into hi + lo floats, so
-//     dx = (xh - cxh) + (xl - cxl) keeps ~2^-24 RELATIVE accuracy even at EPSG:2284 magnitudes
-//     (1.2e7 ft, where a plain float has a 1 ft ulp);
-//   * distances, powers and the per-tile partial sums are FP32; every 512-point tile the partial sums
-//     are promoted into FP64 accumulators, so the error does not grow with the number of points;
-//   * p = 2 shares ONE MUFU.RCP between two points: 1/a + 1/b = (a+b)/(ab), w0/a + w1/b = (w0 b + w1 a)/(ab)
-//     -- this halves MUFU pressure and makes the FP32 FMA pipe the bound instead of the MUFU pipe;
-//   * other exponents use MUFU.RCP / MUFU.RSQ ladders or ex2(c * lg2 d2).
-// Stated accuracy: ~1e-5 relative (tests use 2e-5 on the scale sum|w|h / sum h); distances must stay
-// inside (3e-10, 4e9) units for the paired p = 2 kernel (product of two squared distances in FP32).
+// Same tile driver and TMA point pipeline as the FP64 kernels (idw_kernels.cuh); what changes:
+//   * coordinates become CTA-local: every staged FP64 tile is re-expressed relative to the centre of the CTA's cell
+//     tile (one FP64 subtract per point and CTA) and split into hi + lo floats, so dx keeps ~2^-24 RELATIVE accuracy
+//     even at EPSG:2284 magnitudes (1.2e7 ft, where a plain float has a 1 ft ulp);
+//   * distances, powers and the per-tile partial sums are FP32; every 512-point tile the partial sums are promoted
+//     into FP64 accumulators, so the error does not grow with the number of points.
+// p = 2 (the headline exponent) runs the PACKED body: sm_100's two-wide FP32 instructions (fma.rn.f32x2 / add / mul,
+// SASS FFMA2 / FADD2 / FMUL2) over pairs of adjacent-in-register columns.  The packed forms do not raise the FP32
+// pipe's flop rate (measured: FFMA2 issues at half the FFMA rate, profiles/r2_ubench.txt) -- they halve the ISSUE
+// slots, and the round-1 kernel was issue-bound (7.5 instructions per pair).  To make every operand naturally
+// two-wide:
+//   - coordinates are measured in CELLS from the tile centre (x' = (x - ox) / x_step in FP64 per point and CTA), so
+//     the cell offsets are small integers, exact in FP32, and need no lo part; y' is scaled back by y_step / x_step
+//     when the steps differ.  Weights then carry a constant factor x_step^2 that cancels in num / den;
+//   - per-point values are stored duplicated (v, v) in shared memory, so one LDS.64 delivers a two-wide operand;
+//   - two points still share ONE MUFU.RCP: 1/a + 1/b = (a+b)/(ab), w0/a + w1/b = (w0 b + w1 a)/(ab);
+//     per two cells x two points: 8 packed instructions + 2 MUFU (round 1: 18 scalar + 2 MUFU).
+//   A point tile that is not safe for pairing on this CTA's cells (a*b could leave the FP32 normal range: distances
+//   below 2^-30 or above 2^29 cells) runs through the one-reciprocal packed loop.  Cells that coincide exactly with a
+//   non-key point (reference: NaN) are poisoned afterwards by idw_poison_kernel, which evaluates the coincidence in
+//   FP64 exactly as the reference does.
+// Other exponents use the scalar body: MUFU.RCP / MUFU.RSQ ladders or ex2(c * lg2 d2).
+// Stated accuracy: ~1e-5 relative (tests use 2e-5 on the scale sum|w|h / sum h; bench.py reports the observed maximum).
 #pragma once
 #include "idw_kernels.cuh"
 
@@ -73,95 +84,62 @@ __device__ __forceinline__ void fweights(float d2, const KParams &p, float (&h)[
     }
 }
 
-// PAIRED: p == 2, E == 1 only.
-template <int MODE, int E, int CR, int CC, bool PAIRED, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) idw_fp32_kernel(const __grid_constant__ KParams p) {
-    static_assert(!PAIRED || (MODE == MODE_RCP && E == 1), "pairing is the p = 2 trick");
-    constexpr int WARPS = THREADS / 32;
-    constexpr int T = kTilePoints;
-    constexpr int S = kStages;
-    __shared__ __align__(128) double sm[S][3][T];
-    __shared__ __align__(16) float fx[2][T], fy[2][T];  // [0] = hi, [1] = lo
-    __shared__ __align__(16) float fw[T];
-    __shared__ __align__(8) uint64_t full[S];
+// ---------------------------------------------------------------------------- scalar body (all exponent classes)
+template <int MODE, int E, int CR, int CC, int THREADS_>
+struct Fp32Body {
+    static constexpr int THREADS = THREADS_;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int NACC = 2 * E * CR * CC;
+    static constexpr int T = kTilePoints;
+    static constexpr int BODY_BYTES = 5 * T * (int)sizeof(float);  // fx hi/lo, fy hi/lo, fw
 
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const long long c0 = (long long)blockIdx.x * (32 * CC);
-    const long long r0 = p.row0 + (long long)blockIdx.y * (WARPS * CR);
-    const long long c_base = c0 + lane;
-    const long long r_base = r0 + (long long)warp * CR;
-    // CTA-local origin = centre node of the CTA tile, computed like RCToPoint (tools/utils.go:78-82)
-    const double ox = __dadd_rn(p.x_min, __dmul_rn((double)(c0 + 16 * CC), p.x_step));
-    const double oy = __dadd_rn(p.y_min, __dmul_rn((double)(r0 + (WARPS * CR) / 2), p.y_step));
-
+    double acc[NACC];
     float cxh[CC], cxl[CC], cyh[CR], cyl[CR];
-#pragma unroll
-    for (int b = 0; b < CC; ++b) {
-        double v = __dadd_rn(p.x_min, __dmul_rn((double)(c_base + 32 * b), p.x_step)) - ox;
-        cxh[b] = (float)v;
-        cxl[b] = (float)(v - (double)cxh[b]);
-    }
-#pragma unroll
-    for (int a = 0; a < CR; ++a) {
-        double v = __dadd_rn(p.y_min, __dmul_rn((double)(r_base + a), p.y_step)) - oy;
-        cyh[a] = (float)v;
-        cyl[a] = (float)(v - (double)cyh[a]);
+    int tile_r, tile_c;
+    double ox, oy;  // CTA-local origin = centre node of the CTA tile
+    float *fxh, *fxl, *fyh, *fyl, *fw;
+
+    __device__ __forceinline__ Fp32Body(const KParams &, unsigned char *smem) {
+        float *f = reinterpret_cast<float *>(smem + kStageBytes + kCtrlBytes);
+        fxh = f; fxl = f + T; fyh = f + 2 * T; fyl = f + 3 * T; fw = f + 4 * T;
     }
 
-    double num[E][CR][CC], den[E][CR][CC];
+    __device__ __forceinline__ void setup(const KParams &p, int tr, int tc) {
+        tile_r = tr;
+        tile_c = tc;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const long long r0 = p.row0 + (long long)tile_r * (WARPS * CR), c0 = (long long)tile_c * (32 * CC);
+        const long long c_base = c0 + lane, r_base = r0 + (long long)warp * CR;
+        // origin computed like RCToPoint (tools/utils.go:78-82)
+        ox = __dadd_rn(p.x_min, __dmul_rn((double)(c0 + 16 * CC), p.x_step));
+        oy = __dadd_rn(p.y_min, __dmul_rn((double)(r0 + (WARPS * CR) / 2), p.y_step));
 #pragma unroll
-    for (int e = 0; e < E; ++e)
-#pragma unroll
-        for (int a = 0; a < CR; ++a)
-#pragma unroll
-            for (int b = 0; b < CC; ++b) { num[e][a][b] = 0.0; den[e][a][b] = 0.0; }
-
-    const long long ntiles = (p.n + T - 1) / T;
-    const long long nfull = p.n / T;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    auto issue = [&](long long t) {
-        const int s = (int)(t % S);
-        mbar_expect_tx(&full[s], 3u * T * (uint32_t)sizeof(double));
-        tma_load_1d(&sm[s][0][0], p.x + t * T, T * (uint32_t)sizeof(double), &full[s]);
-        tma_load_1d(&sm[s][1][0], p.y + t * T, T * (uint32_t)sizeof(double), &full[s]);
-        tma_load_1d(&sm[s][2][0], p.w + t * T, T * (uint32_t)sizeof(double), &full[s]);
-    };
-    if (threadIdx.x == 0)
-        for (long long t = 0; t < S - 1 && t < nfull; ++t) issue(t);
-
-    for (long long t = 0; t < ntiles; ++t) {
-        const int s = (int)(t % S);
-        int cnt = T;
-        if (threadIdx.x == 0 && t + S - 1 < nfull) issue(t + S - 1);
-        if (t < nfull) {
-            mbar_wait(&full[s], (uint32_t)((t / S) & 1));
-        } else {
-            cnt = (int)(p.n - t * T);
-            for (int i = threadIdx.x; i < cnt; i += THREADS) {
-                sm[s][0][i] = p.x[t * T + i];
-                sm[s][1][i] = p.y[t * T + i];
-                sm[s][2][i] = p.w[t * T + i];
-            }
-            __syncthreads();
+        for (int b = 0; b < CC; ++b) {
+            double v = __dadd_rn(p.x_min, __dmul_rn((double)(c_base + 32 * b), p.x_step)) - ox;
+            cxh[b] = (float)v;
+            cxl[b] = (float)(v - (double)cxh[b]);
         }
-        // FP64 tile -> CTA-local hi/lo floats (the previous tile's readers left at the trailing barrier)
+#pragma unroll
+        for (int a = 0; a < CR; ++a) {
+            double v = __dadd_rn(p.y_min, __dmul_rn((double)(r_base + a), p.y_step)) - oy;
+            cyh[a] = (float)v;
+            cyl[a] = (float)(v - (double)cyh[a]);
+        }
+    }
+
+    __device__ __forceinline__ void points(const KParams &p, const double *sx, const double *sy, const double *sw, int cnt,
+                                           Ctrl *, unsigned) {
+        // FP64 tile -> CTA-local hi/lo floats (the previous tile's readers left at the driver's trailing barrier)
         for (int i = threadIdx.x; i < cnt; i += THREADS) {
-            double vx = sm[s][0][i] - ox, vy = sm[s][1][i] - oy;
+            double vx = sx[i] - ox, vy = sy[i] - oy;
             float hx = (float)vx, hy = (float)vy;
-            fx[0][i] = hx;
-            fx[1][i] = (float)(vx - (double)hx);
-            fy[0][i] = hy;
-            fy[1][i] = (float)(vy - (double)hy);
-            fw[i] = (float)sm[s][2][i];
+            fxh[i] = hx;
+            fxl[i] = (float)(vx - (double)hx);
+            fyh[i] = hy;
+            fyl[i] = (float)(vy - (double)hy);
+            fw[i] = (float)sw[i];
         }
         __syncthreads();
-
         float pn[E][CR][CC], pd[E][CR][CC];
 #pragma unroll
         for (int e = 0; e < E; ++e)
@@ -169,46 +147,9 @@ __global__ void __launch_bounds__(THREADS, MINB) idw_fp32_kernel(const __grid_co
             for (int a = 0; a < CR; ++a)
 #pragma unroll
                 for (int b = 0; b < CC; ++b) { pn[e][a][b] = 0.f; pd[e][a][b] = 0.f; }
-
-        int i = 0;
-        if constexpr (PAIRED) {
 #pragma unroll 1
-            for (; i + 1 < cnt; i += 2) {
-                const float2 xh = *reinterpret_cast<const float2 *>(&fx[0][i]);
-                const float2 xl = *reinterpret_cast<const float2 *>(&fx[1][i]);
-                const float2 yh = *reinterpret_cast<const float2 *>(&fy[0][i]);
-                const float2 yl = *reinterpret_cast<const float2 *>(&fy[1][i]);
-                const float2 w = *reinterpret_cast<const float2 *>(&fw[i]);
-                float ax[CC], bx[CC], ay[CR], by[CR];
-#pragma unroll
-                for (int b = 0; b < CC; ++b) {
-                    float d0 = (xh.x - cxh[b]) + (xl.x - cxl[b]);
-                    float d1 = (xh.y - cxh[b]) + (xl.y - cxl[b]);
-                    ax[b] = d0 * d0;
-                    bx[b] = d1 * d1;
-                }
-#pragma unroll
-                for (int a = 0; a < CR; ++a) {
-                    float d0 = (yh.x - cyh[a]) + (yl.x - cyl[a]);
-                    float d1 = (yh.y - cyh[a]) + (yl.y - cyl[a]);
-                    ay[a] = d0 * d0;
-                    by[a] = d1 * d1;
-                }
-#pragma unroll
-                for (int a = 0; a < CR; ++a)
-#pragma unroll
-                    for (int b = 0; b < CC; ++b) {
-                        const float A = ax[b] + ay[a], B = bx[b] + by[a];
-                        const float r = frcp(A * B);
-                        const float N = fmaf(w.x, B, w.y * A);
-                        pn[0][a][b] = fmaf(N, r, pn[0][a][b]);
-                        pd[0][a][b] = fmaf(A + B, r, pd[0][a][b]);
-                    }
-            }
-        }
-#pragma unroll 1
-        for (; i < cnt; ++i) {
-            const float xh = fx[0][i], xl = fx[1][i], yh = fy[0][i], yl = fy[1][i], w = fw[i];
+        for (int i = 0; i < cnt; ++i) {
+            const float xh = fxh[i], xl = fxl[i], yh = fyh[i], yl = fyl[i], w = fw[i];
             float dx2[CC], dy2[CR];
 #pragma unroll
             for (int b = 0; b < CC; ++b) { float d = (xh - cxh[b]) + (xl - cxl[b]); dx2[b] = d * d; }
@@ -233,24 +174,207 @@ __global__ void __launch_bounds__(THREADS, MINB) idw_fp32_kernel(const __grid_co
 #pragma unroll
             for (int a = 0; a < CR; ++a)
 #pragma unroll
-                for (int b = 0; b < CC; ++b) { num[e][a][b] += (double)pn[e][a][b]; den[e][a][b] += (double)pd[e][a][b]; }
-        __syncthreads();
+                for (int b = 0; b < CC; ++b) {
+                    acc[((e * CR + a) * CC + b) * 2] += (double)pn[e][a][b];
+                    acc[((e * CR + a) * CC + b) * 2 + 1] += (double)pd[e][a][b];
+                }
     }
 
-    const long long row_end = p.row0 + p.nrows;
+    __device__ __forceinline__ void store(const KParams &p) {
+        const long long row_end = p.row0 + p.nrows;
+        const long long r_base = p.row0 + (long long)tile_r * (WARPS * CR) + (threadIdx.x >> 5) * CR;
+        const long long c_base = (long long)tile_c * (32 * CC) + (threadIdx.x & 31);
 #pragma unroll
-    for (int a = 0; a < CR; ++a) {
-        const long long r = r_base + a;
-        if (r >= row_end) continue;
+        for (int a = 0; a < CR; ++a) {
+            const long long r = r_base + a;
+            if (r >= row_end) continue;
 #pragma unroll
-        for (int b = 0; b < CC; ++b) {
-            const long long c = c_base + 32 * b;
-            if (c >= p.cols) continue;
+            for (int b = 0; b < CC; ++b) {
+                const long long c = c_base + 32 * b;
+                if (c >= p.cols) continue;
 #pragma unroll
-            for (int e = 0; e < E; ++e)
-                p.out[(long long)e * p.plane + (r - p.row0) * p.cols + c] = num[e][a][b] / den[e][a][b];
+                for (int e = 0; e < E; ++e)
+                    p.out[(long long)e * p.plane + (r - p.row0) * p.cols + c] =
+                        acc[((e * CR + a) * CC + b) * 2] / acc[((e * CR + a) * CC + b) * 2 + 1];
+            }
         }
     }
+};
+
+template <int MODE, int E, int CR, int CC, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) idw_fp32_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Fp32Body<MODE, E, CR, CC, THREADS> body(p, smem);
+    tile_driver(p, body, smem);
+}
+
+// ---------------------------------------------------------------------------- packed body (p = 2)
+__device__ __forceinline__ float2 f2dup(float v) { return make_float2(v, v); }
+
+template <int CR, int CC, bool ISO, int THREADS_>
+struct Fp32PackedBody {
+    static_assert(CC % 2 == 0, "columns are processed in pairs");
+    static constexpr int THREADS = THREADS_;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int CP = CC / 2;                 // column pairs per thread
+    static constexpr int NACC = 2 * CR * CC;          // acc[(a*CC + b)*2 + {0: num, 1: den}]
+    static constexpr int T = kTilePoints;
+    static constexpr int BODY_BYTES = 5 * T * (int)sizeof(float2);  // (v, v) pairs: x hi, x lo, y hi, y lo, w
+    static constexpr int W = 32 * CC, H = WARPS * CR; // CTA tile in cells
+
+    double acc[NACC];
+    float2 nkx[CP];   // minus the column offsets (cells from the tile centre) of columns (2j, 2j+1)
+    float2 nky[CR];   // minus the row offset, duplicated
+    int tile_r, tile_c;
+    double ox, oy;    // centre node of the CTA tile
+    float2 *fxh, *fxl, *fyh, *fyl, *fw;
+
+    __device__ __forceinline__ Fp32PackedBody(const KParams &, unsigned char *smem) {
+        float2 *f = reinterpret_cast<float2 *>(smem + kStageBytes + kCtrlBytes);
+        fxh = f; fxl = f + T; fyh = f + 2 * T; fyl = f + 3 * T; fw = f + 4 * T;
+    }
+
+    __device__ __forceinline__ void setup(const KParams &p, int tr, int tc) {
+        tile_r = tr;
+        tile_c = tc;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const long long r0 = p.row0 + (long long)tile_r * H, c0 = (long long)tile_c * W;
+        ox = __dadd_rn(p.x_min, __dmul_rn((double)(c0 + W / 2), p.x_step));
+        oy = __dadd_rn(p.y_min, __dmul_rn((double)(r0 + H / 2), p.y_step));
+#pragma unroll
+        for (int j = 0; j < CP; ++j)
+            nkx[j] = make_float2(-(float)(lane + 64 * j - W / 2), -(float)(lane + 64 * j + 32 - W / 2));
+#pragma unroll
+        for (int a = 0; a < CR; ++a) nky[a] = f2dup(-(float)(warp * CR + a - H / 2));
+    }
+
+    __device__ __forceinline__ void points(const KParams &p, const double *sx, const double *sy, const double *sw, int cnt,
+                                           Ctrl *ctrl, unsigned it) {
+        const int slot = it & 1;
+        const double rho = ISO ? 1.0 : p.y_step * p.inv_x_step;  // y cells -> x cells
+        // FP64 tile -> cell units from the tile centre, hi + lo floats, stored duplicated; and the pairing guard
+        bool unsafe = false;
+        for (int i = threadIdx.x; i < cnt; i += THREADS) {
+            const double vx = (sx[i] - ox) * p.inv_x_step, vy = (sy[i] - oy) * p.inv_y_step;
+            const float hx = (float)vx, hy = (float)vy;
+            fxh[i] = f2dup(hx);
+            fxl[i] = f2dup((float)(vx - (double)hx));
+            fyh[i] = f2dup(hy);
+            fyl[i] = f2dup((float)(vy - (double)hy));
+            fw[i] = f2dup((float)sw[i]);
+            // nearest / farthest cell of the tile along each axis (cells sit at the integers -W/2 .. W/2-1)
+            const double kx = fmin(fmax(rint(vx), -(double)(W / 2)), (double)(W / 2 - 1));
+            const double ky = fmin(fmax(rint(vy), -(double)(H / 2)), (double)(H / 2 - 1));
+            const double nx = fabs(vx - kx), ny = fabs(vy - ky) * rho;
+            const double fx = fmax(fabs(vx + W / 2), fabs(vx - (W / 2 - 1))), fy = fmax(fabs(vy + H / 2), fabs(vy - (H / 2 - 1))) * rho;
+            const bool safe = (nx >= 0x1p-30 || ny >= 0x1p-30) && fx <= 0x1p+29 && fy <= 0x1p+29;
+            unsafe |= !safe;
+        }
+        if (unsafe) ctrl->guard[slot] = 1;
+        __syncthreads();
+        const bool paired_ok = !ctrl->guard[slot];
+        if (threadIdx.x == 0) ctrl->guard[slot ^ 1] = 0;
+        const float2 rho2 = f2dup((float)rho);
+
+        float2 pn[CR][CP], pd[CR][CP];
+#pragma unroll
+        for (int a = 0; a < CR; ++a)
+#pragma unroll
+            for (int j = 0; j < CP; ++j) { pn[a][j] = make_float2(0.f, 0.f); pd[a][j] = make_float2(0.f, 0.f); }
+
+        // squared row distance (duplicated) and column distance (two columns) of one point
+        auto row_sq = [&](float2 yh, float2 yl, int a) {
+            float2 d = __fadd2_rn(__fadd2_rn(yh, nky[a]), yl);
+            if constexpr (!ISO) d = __fmul2_rn(d, rho2);
+            return __fmul2_rn(d, d);
+        };
+        auto col_d = [&](float2 xh, float2 xl, int j) { return __fadd2_rn(__fadd2_rn(xh, nkx[j]), xl); };
+
+        int i = 0;
+        if (paired_ok) {
+#pragma unroll 1
+            for (; i + 1 < cnt; i += 2) {
+                const float4 xh = *reinterpret_cast<const float4 *>(fxh + i), xl = *reinterpret_cast<const float4 *>(fxl + i);
+                const float4 yh = *reinterpret_cast<const float4 *>(fyh + i), yl = *reinterpret_cast<const float4 *>(fyl + i);
+                const float4 w = *reinterpret_cast<const float4 *>(fw + i);
+                const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
+                float2 dx0[CP], dx1[CP], ay[CR], by[CR];
+#pragma unroll
+                for (int j = 0; j < CP; ++j) {
+                    dx0[j] = col_d(make_float2(xh.x, xh.y), make_float2(xl.x, xl.y), j);
+                    dx1[j] = col_d(make_float2(xh.z, xh.w), make_float2(xl.z, xl.w), j);
+                }
+#pragma unroll
+                for (int a = 0; a < CR; ++a) {
+                    ay[a] = row_sq(make_float2(yh.x, yh.y), make_float2(yl.x, yl.y), a);
+                    by[a] = row_sq(make_float2(yh.z, yh.w), make_float2(yl.z, yl.w), a);
+                }
+#pragma unroll
+                for (int a = 0; a < CR; ++a)
+#pragma unroll
+                    for (int j = 0; j < CP; ++j) {
+                        const float2 A = __ffma2_rn(dx0[j], dx0[j], ay[a]), B = __ffma2_rn(dx1[j], dx1[j], by[a]);
+                        const float2 P = __fmul2_rn(A, B);
+                        const float2 r = make_float2(frcp(P.x), frcp(P.y));
+                        const float2 N = __ffma2_rn(w0, B, __fmul2_rn(w1, A));
+                        pn[a][j] = __ffma2_rn(N, r, pn[a][j]);
+                        pd[a][j] = __ffma2_rn(__fadd2_rn(A, B), r, pd[a][j]);
+                    }
+            }
+        }
+#pragma unroll 1
+        for (; i < cnt; ++i) {  // one reciprocal per pair: odd tail, or a tile that is not safe for pairing
+            const float2 xh = fxh[i], xl = fxl[i], yh = fyh[i], yl = fyl[i], w = fw[i];
+            float2 ay[CR];
+#pragma unroll
+            for (int a = 0; a < CR; ++a) ay[a] = row_sq(yh, yl, a);
+#pragma unroll
+            for (int j = 0; j < CP; ++j) {
+                const float2 dx = col_d(xh, xl, j);
+#pragma unroll
+                for (int a = 0; a < CR; ++a) {
+                    const float2 A = __ffma2_rn(dx, dx, ay[a]);
+                    const float2 r = make_float2(frcp(A.x), frcp(A.y));
+                    pn[a][j] = __ffma2_rn(w, r, pn[a][j]);
+                    pd[a][j] = __fadd2_rn(pd[a][j], r);
+                }
+            }
+        }
+        // promote the tile's partial sums
+#pragma unroll
+        for (int a = 0; a < CR; ++a)
+#pragma unroll
+            for (int j = 0; j < CP; ++j) {
+                acc[(a * CC + 2 * j) * 2] += (double)pn[a][j].x;
+                acc[(a * CC + 2 * j) * 2 + 1] += (double)pd[a][j].x;
+                acc[(a * CC + 2 * j + 1) * 2] += (double)pn[a][j].y;
+                acc[(a * CC + 2 * j + 1) * 2 + 1] += (double)pd[a][j].y;
+            }
+    }
+
+    __device__ __forceinline__ void store(const KParams &p) {
+        const long long row_end = p.row0 + p.nrows;
+        const long long r_base = p.row0 + (long long)tile_r * H + (threadIdx.x >> 5) * CR;
+        const long long c_base = (long long)tile_c * W + (threadIdx.x & 31);
+#pragma unroll
+        for (int a = 0; a < CR; ++a) {
+            const long long r = r_base + a;
+            if (r >= row_end) continue;
+#pragma unroll
+            for (int b = 0; b < CC; ++b) {
+                const long long c = c_base + 32 * b;
+                if (c >= p.cols) continue;
+                p.out[(r - p.row0) * p.cols + c] = acc[(a * CC + b) * 2] / acc[(a * CC + b) * 2 + 1];
+            }
+        }
+    }
+};
+
+template <int CR, int CC, bool ISO, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) idw_fp32_packed_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Fp32PackedBody<CR, CC, ISO, THREADS> body(p, smem);
+    tile_driver(p, body, smem);
 }
 
 }  // namespace v2r

@@ -4,6 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -11,6 +14,8 @@
 #include "idw_kernels.cuh"
 
 namespace v2r {
+
+static const double kLgHost[3] = {1.4426950408889634074, -0.72134758493810647712, 0.48089839855788806054};  // = kLg (idw_math.cuh)
 
 // ------------------------------------------------------------------------------------------
 // Sweep classification.  The host accumulates exponents in FP64
@@ -20,7 +25,7 @@ static bool is_int(double v) { return std::floor(v) == v; }
 
 int plan_sweep(const double *exps, int n_exps, std::vector<Pass> &passes) {
     passes.clear();
-    if (!exps || n_exps < 1 || n_exps > 64) return set_error(V2R_IDW_EINVAL, "n_exps must be in [1, 64]");
+    if (!exps || n_exps < 1 || n_exps > kMaxSweep) return set_error(V2R_IDW_EINVAL, "n_exps must be in [1, %d]", kMaxSweep);
     for (int e = 0; e < n_exps; ++e)
         if (!std::isfinite(exps[e])) return set_error(V2R_IDW_EINVAL, "exponent %d is not finite", e);
 
@@ -40,10 +45,12 @@ int plan_sweep(const double *exps, int n_exps, std::vector<Pass> &passes) {
             ps.mode = MODE_GEN;
             ps.first = e0;
             ps.count = len;
-            ps.k0 = 1;  // "safe" pass: every exponent in (0, 3.75] (see weights<MODE_GEN>)
+            ps.k0 = GEN_SINGLE;  // every exponent in (0, 1.99]; else GEN_SAFE (0, 3.75]; else GEN_ANY (see GenKind)
             for (int i = 0; i < len; ++i) {
-                ps.cexp[i] = -exps[e0 + i] / 2.0;
-                if (!(exps[e0 + i] > 0.0 && exps[e0 + i] <= 3.75)) ps.k0 = 0;
+                const double p = exps[e0 + i];
+                ps.cexp[i] = -p / 2.0;
+                if (!(p > 0.0 && p <= 3.75)) ps.k0 = GEN_ANY;
+                else if (p > 1.99 && ps.k0 == GEN_SINGLE) ps.k0 = GEN_SAFE;
             }
             passes.push_back(ps);
             e0 += len;
@@ -89,18 +96,25 @@ int plan_sweep(const double *exps, int n_exps, std::vector<Pass> &passes) {
 // Kernel table
 // ------------------------------------------------------------------------------------------
 struct Variant {
-    int mode, E, k0, dk;  // k0 == 0: runtime ladder
+    int mode, E, k0, dk;  // k0 == 0: runtime ladder (general class: k0 = GenKind)
     int cr, cc, threads;
     void (*fn)(const KParams);
     const char *name;
     bool paired;
     const char *tag;  // non-null: tuning build, selected only by V2R_IDW_TUNE=<tag>
+    int smem;         // dynamic shared memory per CTA
 };
 
-#define V2R_VARIANT(MODE, E, CR, CC, K0, DK, THREADS, MINB) \
-    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE, false, nullptr }
-#define V2R_TUNE(TAG, MODE, E, CR, CC, K0, DK, THREADS, MINB) \
-    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE, false, TAG }
+#define V2R_SMEM(MODE, E, CR, CC, THREADS) smem_bytes((MODE) == MODE_GEN ? (int)sizeof(GenTables) : 0, 2 * (E) * (CR) * (CC), THREADS)
+#define V2R_VARIANT(MODE, E, CR, CC, K0, DK, THREADS, MINB)                                                                     \
+    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE, false, nullptr, \
+              V2R_SMEM(MODE, E, CR, CC, THREADS) }
+#define V2R_TUNE(TAG, MODE, E, CR, CC, K0, DK, THREADS, MINB)                                                               \
+    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE, false, TAG, \
+              V2R_SMEM(MODE, E, CR, CC, THREADS) }
+#define V2R_PAIRED(TAG, CR, CC, THREADS, MINB)                                                                                    \
+    Variant { MODE_RCP, 1, 1, 0, CR, CC, THREADS, idw_fp64_kernel<MODE_RCP, 1, CR, CC, 1, 0, THREADS, MINB, 1>, "MODE_RCP", true, TAG, \
+              V2R_SMEM(MODE_RCP, 1, CR, CC, THREADS) }
 
 // Cell block per thread shrinks as E grows (2*E*CR*CC FP64 accumulators live in registers).
 #define V2R_ROW(MODE)                                                                                  \
@@ -109,18 +123,21 @@ struct Variant {
         V2R_VARIANT(MODE, 5, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE, 6, 2, 2, 0, 0, 256, 1),            \
         V2R_VARIANT(MODE, 7, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE, 8, 2, 2, 0, 0, 256, 1),            \
         V2R_VARIANT(MODE, 9, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE, 10, 2, 2, 0, 0, 256, 1)
+#define V2R_GEN_ROW(KIND)                                                                                    \
+    V2R_VARIANT(MODE_GEN, 1, 2, 4, KIND, 0, 256, 2), V2R_VARIANT(MODE_GEN, 2, 2, 2, KIND, 0, 256, 2),        \
+        V2R_VARIANT(MODE_GEN, 3, 2, 2, KIND, 0, 256, 2), V2R_VARIANT(MODE_GEN, 4, 2, 2, KIND, 0, 256, 2)
+#define V2R_GEN_ROW_HI(KIND)                                                                                 \
+    V2R_VARIANT(MODE_GEN, 5, 2, 2, KIND, 0, 256, 1), V2R_VARIANT(MODE_GEN, 6, 2, 2, KIND, 0, 256, 1),        \
+        V2R_VARIANT(MODE_GEN, 7, 2, 2, KIND, 0, 256, 1), V2R_VARIANT(MODE_GEN, 8, 2, 2, KIND, 0, 256, 1),    \
+        V2R_VARIANT(MODE_GEN, 9, 2, 2, KIND, 0, 256, 1), V2R_VARIANT(MODE_GEN, 10, 2, 2, KIND, 0, 256, 1)
 
 static const Variant kVariants[] = {
-    // compile-time ladders for the headline shapes (looked up first)
     // tuning builds (V2R_IDW_TUNE=<tag>), kept to document what was measured; never picked by default
-    V2R_TUNE("t384", MODE_RCP, 1, 4, 4, 1, 0, 384, 1), V2R_TUNE("t384", MODE_QRT, 1, 4, 4, 3, 0, 384, 1),
-    V2R_TUNE("b2", MODE_RCP, 1, 4, 2, 1, 0, 256, 2), V2R_TUNE("b2", MODE_QRT, 9, 1, 2, 1, 1, 256, 2),
-    V2R_TUNE("c1x4", MODE_QRT, 9, 1, 4, 1, 1, 256, 1), V2R_TUNE("c4x4", MODE_QRT, 1, 4, 4, 3, 0, 256, 1),
-    V2R_TUNE("g2x2", MODE_GEN, 1, 2, 2, 1, 0, 256, 2), V2R_TUNE("g4x4", MODE_GEN, 1, 4, 4, 1, 0, 256, 1),
-    Variant{MODE_RCP, 1, 1, 0, 6, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 6, 4, 1, 0, 256, 1, 1>, "MODE_RCP", true, "c6x4"},
-    Variant{MODE_RCP, 1, 1, 0, 4, 6, 256, idw_fp64_kernel<MODE_RCP, 1, 4, 6, 1, 0, 256, 1, 1>, "MODE_RCP", true, "c4x6"},
-    Variant{MODE_RCP, 1, 1, 0, 5, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 5, 4, 1, 0, 256, 1, 1>, "MODE_RCP", true, "c5x4"},
-    Variant{MODE_RCP, 1, 1, 0, 4, 4, 256, idw_fp64_kernel<MODE_RCP, 1, 4, 4, 1, 0, 256, 1, 1>, "MODE_RCP", true, nullptr},  // p = 2, paired (c2, c4)
+    V2R_TUNE("g2x2", MODE_GEN, 1, 2, 2, GEN_SINGLE, 0, 256, 2), V2R_TUNE("g4x4", MODE_GEN, 1, 4, 4, GEN_SINGLE, 0, 256, 1),
+    V2R_TUNE("g4x2", MODE_GEN, 1, 4, 2, GEN_SINGLE, 0, 256, 2),
+    V2R_PAIRED("c4x6", 4, 6, 256, 1),
+    // compile-time ladders for the headline shapes (looked up first)
+    V2R_PAIRED(nullptr, 4, 4, 256, 1),              // p = 2, paired (c2, c4)
     V2R_VARIANT(MODE_RCP, 1, 4, 4, 1, 0, 256, 1),   // p = 2, one reciprocal per pair (V2R_IDW_FP64_PAIRED=0)
     // rsqrt / root4 bases have longer dependent chains: 2x4 cells at two CTAs per SM measured +8 % over 4x4 at one
     V2R_VARIANT(MODE_RSQ, 1, 2, 4, 1, 0, 256, 2),   // p = 1
@@ -131,18 +148,10 @@ static const Variant kVariants[] = {
     V2R_VARIANT(MODE_QRT, 4, 2, 2, 2, 1, 256, 2),   // p = 1, 1.5, 2, 2.5       (config c5)
     // runtime ladders
     V2R_ROW(MODE_RCP), V2R_ROW(MODE_RSQ), V2R_ROW(MODE_QRT),
-    // general exponents, all in (0, 3.75]: no zero/overflow handling beyond one range test (K0 = 1 marks them)
-    V2R_VARIANT(MODE_GEN, 1, 2, 4, 1, 0, 256, 2), V2R_VARIANT(MODE_GEN, 2, 2, 2, 1, 0, 256, 2),
-    V2R_VARIANT(MODE_GEN, 3, 2, 2, 1, 0, 256, 2), V2R_VARIANT(MODE_GEN, 4, 2, 2, 1, 0, 256, 2),
-    V2R_VARIANT(MODE_GEN, 5, 2, 2, 1, 0, 256, 1), V2R_VARIANT(MODE_GEN, 6, 2, 2, 1, 0, 256, 1),
-    V2R_VARIANT(MODE_GEN, 7, 2, 2, 1, 0, 256, 1), V2R_VARIANT(MODE_GEN, 8, 2, 2, 1, 0, 256, 1),
-    V2R_VARIANT(MODE_GEN, 9, 2, 2, 1, 0, 256, 1), V2R_VARIANT(MODE_GEN, 10, 2, 2, 1, 0, 256, 1),
-    // general exponents, any value (p <= 0, large p): saturating log2 / clamped exp2
-    V2R_VARIANT(MODE_GEN, 1, 2, 4, 0, 0, 256, 2), V2R_VARIANT(MODE_GEN, 2, 2, 2, 0, 0, 256, 2),
-    V2R_VARIANT(MODE_GEN, 3, 2, 2, 0, 0, 256, 2), V2R_VARIANT(MODE_GEN, 4, 2, 2, 0, 0, 256, 2),
-    V2R_VARIANT(MODE_GEN, 5, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE_GEN, 6, 2, 2, 0, 0, 256, 1),
-    V2R_VARIANT(MODE_GEN, 7, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE_GEN, 8, 2, 2, 0, 0, 256, 1),
-    V2R_VARIANT(MODE_GEN, 9, 2, 2, 0, 0, 256, 1), V2R_VARIANT(MODE_GEN, 10, 2, 2, 0, 0, 256, 1),
+    // general exponents: all in (0, 1.99] (2^n by an integer add), all in (0, 3.75] (no specials in the loop), any value
+    V2R_GEN_ROW(GEN_SINGLE),
+    V2R_GEN_ROW(GEN_SAFE), V2R_GEN_ROW_HI(GEN_SAFE),
+    V2R_GEN_ROW(GEN_ANY), V2R_GEN_ROW_HI(GEN_ANY),
 };
 
 static const Variant *pick_variant(const Pass &ps) {
@@ -157,7 +166,10 @@ static const Variant *pick_variant(const Pass &ps) {
         if (v.paired && !allow_paired) continue;
         if (v.mode != ps.mode || v.E != ps.count) continue;
         if (v.k0 == ps.k0 && v.dk == ps.dk) return &v;
-        if (ps.mode == MODE_GEN) continue;
+        if (ps.mode == MODE_GEN) {
+            if (ps.k0 == GEN_SINGLE && v.k0 == GEN_SAFE && !fallback) fallback = &v;  // no integer-add build for this E
+            continue;
+        }
         if (v.k0 == 0 && !fallback) fallback = &v;
     }
     return fallback;
@@ -184,7 +196,9 @@ static double model_ops(const Pass &ps, const Variant &v) {
         return hi + m - 1;
     };
     if (ps.mode == MODE_GEN) {
-        ops += 8.0 + 12.0 * E;  // tab_log2 once (8), c*L + tab_exp2_32 per exponent (1 + 11)
+        const double ex = v.k0 == GEN_SINGLE ? 7.0 : 8.0;  // tab_exp2: 3 rounding + 3 series + 1 or 2 scaling
+        if (E == 1 && v.k0 != GEN_ANY) ops += 6.0 + ex;     // folded log2 (5 + the exponent's magic add)
+        else ops += 7.0 + (1.0 + ex) * E;                   // log2 once, c*L + exp2 per exponent
     } else {
         ops += ps.mode == MODE_RCP ? 3 : (ps.mode == MODE_RSQ ? 5 : 7);
         if (v.paired) ops -= 0.5;  // 11 instead of 12 instructions per two pairs
@@ -197,6 +211,103 @@ static double model_ops(const Pass &ps, const Variant &v) {
 static std::atomic<long long> g_launches{0};
 long long launch_count() { return g_launches.load(); }
 void count_launch() { g_launches++; }
+
+// ------------------------------------------------------------------------------------------
+// Per-device facts: SM count, table image of the general class, occupancy of each kernel
+// ------------------------------------------------------------------------------------------
+struct DeviceFacts {
+    int sms = 0;
+    GenTables *tables = nullptr;
+    std::map<const void *, int> ctas_per_sm;  // kernel -> resident CTAs per SM with its shared memory
+    bool pool_ready = false;
+};
+static std::mutex g_facts_mu;
+static std::map<int, DeviceFacts> g_facts;
+
+// resident CTAs of `fn` on the whole device (0 on error, message set)
+int device_slots(int device, const void *fn, int threads, int smem, const GenTables **tables) {
+    std::lock_guard<std::mutex> lk(g_facts_mu);
+    DeviceFacts &f = g_facts[device];
+    if (!f.sms) cudaDeviceGetAttribute(&f.sms, cudaDevAttrMultiProcessorCount, device);
+    if (!f.pool_ready) {  // keep freed scratch in the stream-ordered pool instead of returning it to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        f.pool_ready = true;
+    }
+    if (tables) {
+        if (!f.tables) {
+            static GenTables host;  // identical for every device
+            static bool built = false;
+            if (!built) { build_gen_tables(host); built = true; }
+            if (cudaMalloc((void **)&f.tables, sizeof(GenTables)) != cudaSuccess ||
+                cudaMemcpy(f.tables, &host, sizeof(GenTables), cudaMemcpyHostToDevice) != cudaSuccess) {
+                cudaGetLastError();
+                f.tables = nullptr;
+                set_error(V2R_IDW_ENOMEM, "general-class tables: allocation / upload failed");
+                return 0;
+            }
+        }
+        *tables = f.tables;
+    }
+    auto it = f.ctas_per_sm.find(fn);
+    if (it == f.ctas_per_sm.end()) {
+        cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        int occ = 0;
+        if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, (size_t)smem);
+        if (ce != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            set_error(V2R_IDW_ECUDA, "kernel needs %d bytes of shared memory: %s", smem, ce == cudaSuccess ? "does not fit an SM" : cudaGetErrorString(ce));
+            return 0;
+        }
+        it = f.ctas_per_sm.emplace(fn, occ).first;
+    }
+    return f.sms * it->second;
+}
+
+// Work decomposition of one launch (idw_kernels.cuh): whole tiles for the full waves, (tile, segment) units for the
+// tiles of the last partial wave.  `segs` / `seg_tiles` depend on n only, so a cell's value does not depend on the cut.
+void plan_grid(KParams &kp, int tile_r, int tile_c, int slots) {
+    static const bool tail_split = !(getenv("V2R_IDW_TAIL") && atoi(getenv("V2R_IDW_TAIL")) == 0);
+    const long long tiles_x = (kp.cols + tile_c - 1) / tile_c, tiles_y = (kp.nrows + tile_r - 1) / tile_r;
+    kp.tiles_x = (int)tiles_x;
+    kp.n_tiles = tiles_x * tiles_y;
+    const long long ntp = (kp.n + kTilePoints - 1) / kTilePoints;
+    long long K = std::max<long long>(1, std::min<long long>(ntp, kMaxSegs));
+    const long long seg_tiles = std::max<long long>(1, (ntp + K - 1) / K);
+    K = std::max<long long>(1, (ntp + seg_tiles - 1) / seg_tiles);
+    kp.segs = (int)K;
+    kp.seg_tiles = (int)seg_tiles;
+    const long long R = kp.n_tiles % slots;
+    if (K == 1 || R == 0 || !tail_split) {
+        kp.n_main = kp.n_tiles;
+        kp.n_tail = 0;
+    } else {
+        kp.n_main = kp.n_tiles - R;
+        kp.n_tail = (int)std::min<long long>(slots, R * K);
+    }
+}
+
+// Stream-ordered scratch for the tail tiles: partials, then the arrival counters (zeroed), then one flag word.
+int alloc_scratch(cudaStream_t stream, KParams &kp, int nacc, int threads, void **block, unsigned **flag) {
+    const long long R = kp.n_tiles - kp.n_main;
+    const size_t partial = (size_t)R * kp.segs * nacc * threads * sizeof(double);
+    const size_t words = (size_t)R + 4;
+    cudaError_t ce = cudaMallocAsync(block, partial + words * sizeof(unsigned), stream);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(V2R_IDW_ENOMEM, "cudaMallocAsync(%zu bytes of tail scratch): %s", partial + words * 4, cudaGetErrorString(ce));
+    }
+    kp.scratch = reinterpret_cast<double *>(*block);
+    kp.counters = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(*block) + partial);
+    if (flag) *flag = kp.counters + R;
+    ce = cudaMemsetAsync(kp.counters, 0, words * sizeof(unsigned), stream);
+    if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "cudaMemsetAsync: %s", cudaGetErrorString(ce));
+    return V2R_IDW_OK;
+}
 
 // Exact-hit rule (features/idw/idw_utils.go:13-16): every keyed cell returns its point's weight,
 // for every exponent.  Runs after the main kernel on the same stream.
@@ -224,8 +335,69 @@ int launch_patch_exact(cudaStream_t stream, const double *d_z, const long long *
     return V2R_IDW_OK;
 }
 
+// Kernels without in-loop special cases (general class with positive exponents, packed FP32) rely on this pass for
+// the reference's d == 0 rule on non-key cells (features/idw/idw_utils.go:19-25 with tools/utils.go:166-168:
+// Pow(0, -p) = +Inf, Inf/Inf = NaN): a cell whose squared distance to some point -- evaluated exactly like the
+// kernels and the reference do, point minus node, each square rounded on its own -- is zero or subnormal becomes NaN
+// in the planes [e0, e0 + ne).  A NaN coordinate makes every weight NaN in the reference: it raises *flag and
+// idw_nanfill_kernel then fills those planes.  The exact-hit patch runs afterwards and overrides both.
+__global__ void idw_poison_kernel(const double *__restrict__ x, const double *__restrict__ y, long long n, double x_min,
+                                  double x_step, double y_min, double y_step, long long cols, long long row0, long long nrows,
+                                  double *__restrict__ out, long long plane, int ne, unsigned *flag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double px = x[i], py = y[i];
+    if (px != px || py != py) { if (flag) *flag = 1u; return; }
+    const double qc = rint((px - x_min) / x_step), qr = rint((py - y_min) / y_step);
+    if (!(qc >= -2.0 && qc <= (double)cols + 1.0 && qr >= (double)row0 - 2.0 && qr <= (double)(row0 + nrows) + 1.0)) return;
+    const long long c0 = (long long)qc, r0 = (long long)qr;
+    for (long long r = r0 - 1; r <= r0 + 1; ++r) {
+        if (r < row0 || r >= row0 + nrows) continue;
+        const double dy = __dsub_rn(py, __dadd_rn(y_min, __dmul_rn((double)r, y_step)));
+        const double dy2 = __dmul_rn(dy, dy);
+        for (long long c = c0 - 1; c <= c0 + 1; ++c) {
+            if (c < 0 || c >= cols) continue;
+            const double dx = __dsub_rn(px, __dadd_rn(x_min, __dmul_rn((double)c, x_step)));
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), dy2);
+            if (d2 < 2.2250738585072014e-308)
+                for (int e = 0; e < ne; ++e) out[(long long)e * plane + (r - row0) * cols + c] = __longlong_as_double(0x7ff8000000000000LL);
+        }
+    }
+}
+__global__ void idw_nanfill_kernel(double *__restrict__ out, long long count, const unsigned *flag) {
+    if (*flag == 0u) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+        out[i] = __longlong_as_double(0x7ff8000000000000LL);
+}
 
-int launch_rows_fp64(cudaStream_t stream, const double *d_x, const double *d_y, const double *d_z,
+int launch_poison(cudaStream_t stream, const double *d_x, const double *d_y, long long n, const v2r_idw_grid &g, long long row0,
+                  long long nrows, double *d_out, int ne, unsigned *flag) {
+    if (n <= 0) return V2R_IDW_OK;
+    const int tb = 256;
+    const long long plane = nrows * g.cols;
+    idw_poison_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, stream>>>(d_x, d_y, n, g.x_min, g.x_step, g.y_min, g.y_step, g.cols, row0,
+                                                                      nrows, d_out, plane, ne, flag);
+    g_launches++;
+    if (flag) {
+        const long long count = plane * ne;
+        idw_nanfill_kernel<<<(unsigned)std::min<long long>(4096, (count + tb - 1) / tb), tb, 0, stream>>>(d_out, count, flag);
+        g_launches++;
+    }
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "poison kernel launch: %s", cudaGetErrorString(ce));
+    return V2R_IDW_OK;
+}
+
+void fill_params(KParams &kp, const double *d_x, const double *d_y, const double *d_z, long long n, const v2r_idw_grid &g,
+                 long long row0, long long nrows) {
+    kp.x = d_x; kp.y = d_y; kp.w = d_z; kp.n = n;
+    kp.x_min = g.x_min; kp.x_step = g.x_step; kp.y_min = g.y_min; kp.y_step = g.y_step;
+    kp.inv_x_step = 1.0 / g.x_step; kp.inv_y_step = 1.0 / g.y_step;
+    kp.cols = g.cols; kp.row0 = row0; kp.nrows = nrows;
+    kp.plane = nrows * g.cols;
+}
+
+int launch_rows_fp64(int device, cudaStream_t stream, const double *d_x, const double *d_y, const double *d_z,
                      const long long *d_kr, const long long *d_kc, long long n, const v2r_idw_grid &g,
                      long long row0, long long nrows, const double *exps, int n_exps, double *d_out) {
     std::vector<Pass> passes;
@@ -236,21 +408,34 @@ int launch_rows_fp64(cudaStream_t stream, const double *d_x, const double *d_y, 
         const Variant *v = pick_variant(ps);
         if (!v) return set_error(V2R_IDW_EINVAL, "no kernel variant for mode %d E %d", ps.mode, ps.count);
         KParams kp{};
-        kp.x = d_x; kp.y = d_y; kp.w = d_z; kp.n = n;
-        kp.x_min = g.x_min; kp.x_step = g.x_step; kp.y_min = g.y_min; kp.y_step = g.y_step;
-        kp.cols = g.cols; kp.row0 = row0; kp.nrows = nrows;
+        fill_params(kp, d_x, d_y, d_z, n, g, row0, nrows);
         kp.out = d_out + (long long)ps.first * plane;
-        kp.plane = plane;
         kp.k0 = ps.k0 > 0 ? ps.k0 : 1;
         kp.dk = ps.dk > 0 ? ps.dk : 1;
-        for (int i = 0; i < ps.count; ++i) kp.cexp[i] = 32.0 * ps.cexp[i];  // exact scaling by a power of two
-        const long long tile_r = (long long)(v->threads / 32) * v->cr, tile_c = 32LL * v->cc;
-        const long long gx = (g.cols + tile_c - 1) / tile_c, gy = (nrows + tile_r - 1) / tile_r;
-        if (gx > 2147483647LL || gy > 65535LL)
+        for (int i = 0; i < ps.count; ++i) kp.cexp[i] = kExpScale * ps.cexp[i];  // exact scaling by a power of two
+        for (int i = 0; i < 3; ++i) kp.lg_s[i] = kp.cexp[0] * kLgHost[i];
+        const GenTables *tables = nullptr;
+        const int slots = device_slots(device, (const void *)v->fn, v->threads, v->smem, ps.mode == MODE_GEN ? &tables : nullptr);
+        if (!slots) return V2R_IDW_ECUDA;
+        kp.tables = tables;
+        plan_grid(kp, (v->threads / 32) * v->cr, 32 * v->cc, slots);
+        const long long grid = kp.n_main + kp.n_tail;
+        if (grid > 2147483647LL || kp.n_tiles * kp.segs > 2147483647LL)
             return set_error(V2R_IDW_EINVAL, "band of %lld rows x %lld cols exceeds one launch; use smaller bands", nrows, (long long)g.cols);
-        v->fn<<<dim3((unsigned)gx, (unsigned)gy), v->threads, 0, stream>>>(kp);
+        const bool poison = ps.mode == MODE_GEN && v->k0 != GEN_ANY;
+        void *block = nullptr;
+        unsigned *flag = nullptr;
+        if (kp.n_tail > 0 || poison) {
+            if ((rc = alloc_scratch(stream, kp, 2 * v->E * v->cr * v->cc, v->threads, &block, &flag))) return rc;
+        }
+        v->fn<<<(unsigned)grid, v->threads, v->smem, stream>>>(kp);
         g_launches++;
         cudaError_t ce = cudaGetLastError();
+        if (ce == cudaSuccess && poison) {
+            if ((rc = launch_poison(stream, d_x, d_y, n, g, row0, nrows, kp.out, ps.count, flag))) ce = cudaErrorUnknown;
+        }
+        if (block) cudaFreeAsync(block, stream);
+        if (rc) return rc;
         if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "idw kernel launch: %s", cudaGetErrorString(ce));
     }
     return launch_patch_exact(stream, d_z, d_kr, d_kc, n, g, row0, nrows, d_out, n_exps);
@@ -262,7 +447,7 @@ int validate_geometry(long long n, const v2r_idw_grid *g, long long row0, long l
     if (g->rows < 0 || g->cols < 0) return set_error(V2R_IDW_EINVAL, "negative grid dimensions");
     if (row0 < 0 || nrows < 0 || row0 + nrows > g->rows)
         return set_error(V2R_IDW_EINVAL, "rows [%lld, %lld) outside the grid of %lld rows", row0, row0 + nrows, (long long)g->rows);
-    if (n_exps < 1 || n_exps > 64) return set_error(V2R_IDW_EINVAL, "n_exps must be in [1, 64]");
+    if (n_exps < 1 || n_exps > kMaxSweep) return set_error(V2R_IDW_EINVAL, "n_exps must be in [1, %d]", kMaxSweep);
     return V2R_IDW_OK;
 }
 
@@ -293,9 +478,9 @@ extern "C" int v2r_idw_launch_rows(int device, void *stream, const double *d_x, 
     if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(ce));
     return guarded([&] {
         if (precision == V2R_IDW_FP32)
-            return launch_rows_fp32((cudaStream_t)stream, d_x, d_y, d_z, (const long long *)d_key_r, (const long long *)d_key_c, n,
+            return launch_rows_fp32(device, (cudaStream_t)stream, d_x, d_y, d_z, (const long long *)d_key_r, (const long long *)d_key_c, n,
                                     *grid, row0, nrows, exps, n_exps, d_out);
-        return launch_rows_fp64((cudaStream_t)stream, d_x, d_y, d_z, (const long long *)d_key_r, (const long long *)d_key_c, n,
+        return launch_rows_fp64(device, (cudaStream_t)stream, d_x, d_y, d_z, (const long long *)d_key_r, (const long long *)d_key_c, n,
                                 *grid, row0, nrows, exps, n_exps, d_out);
     });
 }
@@ -317,7 +502,7 @@ extern "C" int v2r_idw_describe(const double *exps, int n_exps, int precision, c
             char tmp[160];
             snprintf(tmp, sizeof tmp, "%sfp64/%s E=%d cells=%dx%d k0=%d dk=%d%s", s.empty() ? "" : " + ", mode_name(ps.mode),
                      ps.count, v->cr, v->cc, ps.k0, ps.dk,
-                     v->tag ? v->tag : (v->paired ? " (paired reciprocal)" : (ps.mode == MODE_GEN ? (v->k0 ? " (0 < p <= 3.75)" : " (any p)") : (v->k0 ? " (static ladder)" : ""))));
+                     v->tag ? v->tag : (v->paired ? " (paired reciprocal)" : (ps.mode == MODE_GEN ? (v->k0 == GEN_SINGLE ? " (0 < p <= 1.99)" : (v->k0 == GEN_SAFE ? " (0 < p <= 3.75)" : " (any p)")) : (v->k0 ? " (static ladder)" : ""))));
             s += tmp;
             ops += model_ops(ps, *v);
         }

@@ -1,6 +1,7 @@
 // idw_launch_fp32.cu -- dispatch of the FP32 fast path (see idw_kernels_fp32.cuh).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -11,38 +12,53 @@ namespace v2r {
 
 struct FVariant {
     int mode, E;
-    bool paired;
+    bool packed, iso;  // packed: the two-wide p = 2 body; iso: x_step == y_step (no row rescaling)
     int cr, cc, threads, minb;
     void (*fn)(const KParams);
+    int smem;
+    const char *tag;  // non-null: tuning build (V2R_IDW_TUNE=<tag>)
 };
 
-#define V2R_FVARIANT(MODE, E, CR, CC, PAIRED, MINB) \
-    FVariant { MODE, E, PAIRED, CR, CC, 256, MINB, idw_fp32_kernel<MODE, E, CR, CC, PAIRED, 256, MINB> }
-#define V2R_FROW(MODE)                                                                                      \
-    V2R_FVARIANT(MODE, 1, 4, 4, false, 2), V2R_FVARIANT(MODE, 2, 2, 4, false, 2),                           \
-        V2R_FVARIANT(MODE, 3, 2, 2, false, 2), V2R_FVARIANT(MODE, 4, 2, 2, false, 2),                       \
-        V2R_FVARIANT(MODE, 5, 1, 2, false, 2), V2R_FVARIANT(MODE, 6, 1, 2, false, 2),                       \
-        V2R_FVARIANT(MODE, 7, 1, 2, false, 2), V2R_FVARIANT(MODE, 8, 1, 2, false, 2),                       \
-        V2R_FVARIANT(MODE, 9, 1, 2, false, 2), V2R_FVARIANT(MODE, 10, 1, 2, false, 2)
+#define V2R_FVARIANT(MODE, E, CR, CC, MINB)                                                           \
+    FVariant { MODE, E, false, false, CR, CC, 256, MINB, idw_fp32_kernel<MODE, E, CR, CC, 256, MINB>, \
+               smem_bytes(Fp32Body<MODE, E, CR, CC, 256>::BODY_BYTES, 2 * (E) * (CR) * (CC), 256), nullptr }
+#define V2R_FPACKED(TAG, CR, CC, ISO, THREADS, MINB)                                                                  \
+    FVariant { MODE_RCP, 1, true, ISO, CR, CC, THREADS, MINB, idw_fp32_packed_kernel<CR, CC, ISO, THREADS, MINB>,     \
+               smem_bytes(Fp32PackedBody<CR, CC, ISO, THREADS>::BODY_BYTES, 2 * (CR) * (CC), THREADS), TAG }
+#define V2R_FROW(MODE)                                                                          \
+    V2R_FVARIANT(MODE, 1, 4, 4, 2), V2R_FVARIANT(MODE, 2, 2, 4, 2),                             \
+        V2R_FVARIANT(MODE, 3, 2, 2, 2), V2R_FVARIANT(MODE, 4, 2, 2, 2),                         \
+        V2R_FVARIANT(MODE, 5, 1, 2, 2), V2R_FVARIANT(MODE, 6, 1, 2, 2),                         \
+        V2R_FVARIANT(MODE, 7, 1, 2, 2), V2R_FVARIANT(MODE, 8, 1, 2, 2),                         \
+        V2R_FVARIANT(MODE, 9, 1, 2, 2), V2R_FVARIANT(MODE, 10, 1, 2, 2)
 
 static const FVariant kFVariants[] = {
-    V2R_FVARIANT(MODE_RCP, 1, 4, 4, true, 1),  // p = 2: two points per MUFU.RCP; one CTA per SM measured 4.6 % faster than two
-    V2R_FVARIANT(MODE_RCP, 1, 4, 4, true, 2),  // (V2R_IDW_FP32_MINB=2 selects the two-CTA build; tuning aid)
+    // tuning builds of the packed p = 2 kernel (cell block, CTAs per SM)
+    V2R_FPACKED("f4x4", 4, 4, true, 256, 1), V2R_FPACKED("f2x8m2", 2, 8, true, 256, 2), V2R_FPACKED("f4x8", 4, 8, true, 256, 1),
+    V2R_FPACKED("f2x16", 2, 16, true, 256, 1),
+    // p = 2: packed FP32 (FFMA2 / FADD2 / FMUL2), two points per MUFU.RCP
+    V2R_FPACKED(nullptr, 2, 8, true, 256, 1), V2R_FPACKED(nullptr, 2, 8, false, 256, 1),
     V2R_FROW(MODE_RCP), V2R_FROW(MODE_RSQ), V2R_FROW(MODE_QRT), V2R_FROW(MODE_GEN),
 };
 
-static const FVariant *pick_fvariant(const Pass &ps) {
-    static const int want_minb = getenv("V2R_IDW_FP32_MINB") ? atoi(getenv("V2R_IDW_FP32_MINB")) : 1;
+static const FVariant *pick_fvariant(const Pass &ps, bool iso) {
+    static const char *tune = getenv("V2R_IDW_TUNE");
+    const bool p2 = ps.mode == MODE_RCP && ps.count == 1 && ps.k0 == 1;
+    if (tune && *tune && p2 && iso)
+        for (const FVariant &v : kFVariants)
+            if (v.tag && !strcmp(v.tag, tune)) return &v;
     for (const FVariant &v : kFVariants) {
-        if (v.paired && v.minb != want_minb) continue;
-        if (v.mode != ps.mode || v.E != ps.count) continue;
-        if (v.paired && !(ps.k0 == 1 && ps.count == 1)) continue;
-        return &v;
+        if (v.tag) continue;
+        if (v.packed) {
+            if (p2 && v.iso == iso) return &v;
+            continue;
+        }
+        if (v.mode == ps.mode && v.E == ps.count) return &v;
     }
     return nullptr;
 }
 
-int launch_rows_fp32(cudaStream_t stream, const double *d_x, const double *d_y, const double *d_z,
+int launch_rows_fp32(int device, cudaStream_t stream, const double *d_x, const double *d_y, const double *d_z,
                      const long long *d_kr, const long long *d_kc, long long n, const v2r_idw_grid &g,
                      long long row0, long long nrows, const double *exps, int n_exps, double *d_out) {
     std::vector<Pass> passes;
@@ -50,24 +66,29 @@ int launch_rows_fp32(cudaStream_t stream, const double *d_x, const double *d_y, 
     if (rc) return rc;
     const long long plane = nrows * g.cols;
     for (const Pass &ps : passes) {
-        const FVariant *v = pick_fvariant(ps);
+        const FVariant *v = pick_fvariant(ps, g.x_step == g.y_step);
         if (!v) return set_error(V2R_IDW_EINVAL, "no FP32 kernel variant for mode %d E %d", ps.mode, ps.count);
         KParams kp{};
-        kp.x = d_x; kp.y = d_y; kp.w = d_z; kp.n = n;
-        kp.x_min = g.x_min; kp.x_step = g.x_step; kp.y_min = g.y_min; kp.y_step = g.y_step;
-        kp.cols = g.cols; kp.row0 = row0; kp.nrows = nrows;
+        fill_params(kp, d_x, d_y, d_z, n, g, row0, nrows);
         kp.out = d_out + (long long)ps.first * plane;
-        kp.plane = plane;
         kp.k0 = ps.k0 > 0 ? ps.k0 : 1;
         kp.dk = ps.dk > 0 ? ps.dk : 1;
         for (int i = 0; i < ps.count; ++i) kp.cexp[i] = ps.cexp[i];
-        const long long tile_r = (long long)(v->threads / 32) * v->cr, tile_c = 32LL * v->cc;
-        const long long gx = (g.cols + tile_c - 1) / tile_c, gy = (nrows + tile_r - 1) / tile_r;
-        if (gx > 2147483647LL || gy > 65535LL)
+        const int slots = device_slots(device, (const void *)v->fn, v->threads, v->smem, nullptr);
+        if (!slots) return V2R_IDW_ECUDA;
+        plan_grid(kp, (v->threads / 32) * v->cr, 32 * v->cc, slots);
+        const long long grid = kp.n_main + kp.n_tail;
+        if (grid > 2147483647LL || kp.n_tiles * kp.segs > 2147483647LL)
             return set_error(V2R_IDW_EINVAL, "band of %lld rows x %lld cols exceeds one launch; use smaller bands", nrows, (long long)g.cols);
-        v->fn<<<dim3((unsigned)gx, (unsigned)gy), v->threads, 0, stream>>>(kp);
+        void *block = nullptr;
+        if (kp.n_tail > 0 && (rc = alloc_scratch(stream, kp, 2 * v->E * v->cr * v->cc, v->threads, &block, nullptr))) return rc;
+        v->fn<<<(unsigned)grid, v->threads, v->smem, stream>>>(kp);
         count_launch();
         cudaError_t ce = cudaGetLastError();
+        // the packed kernel has no d == 0 semantics of its own (coordinates are rescaled): exact coincidences -> NaN here
+        if (ce == cudaSuccess && v->packed) rc = launch_poison(stream, d_x, d_y, n, g, row0, nrows, kp.out, 1, nullptr);
+        if (block) cudaFreeAsync(block, stream);
+        if (rc) return rc;
         if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "idw fp32 kernel launch: %s", cudaGetErrorString(ce));
     }
     return launch_patch_exact(stream, d_z, d_kr, d_kc, n, g, row0, nrows, d_out, n_exps);
@@ -77,10 +98,10 @@ std::string describe_fp32(const std::vector<Pass> &passes) {
     std::string s;
     static const char *names[] = {"rcp", "rsqrt", "root4", "general"};
     for (const Pass &ps : passes) {
-        const FVariant *v = pick_fvariant(ps);
+        const FVariant *v = pick_fvariant(ps, true);
         char tmp[160];
         snprintf(tmp, sizeof tmp, "%sfp32/%s%s E=%d cells=%dx%d k0=%d dk=%d", s.empty() ? "" : " + ", names[ps.mode],
-                 v && v->paired ? " (paired rcp)" : "", ps.count, v ? v->cr : 0, v ? v->cc : 0, ps.k0, ps.dk);
+                 v && v->packed ? " (packed f32x2, paired rcp)" : "", ps.count, v ? v->cr : 0, v ? v->cc : 0, ps.k0, ps.dk);
         s += tmp;
     }
     return s;

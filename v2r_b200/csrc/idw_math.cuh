@@ -1,18 +1,25 @@
 // idw_math.cuh -- the arithmetic of d2^(-p/2): seed-plus-one-cubic-step base powers of the rcp / rsqrt / root4 classes
 // (bottom of the file) and software log2 / exp2 for the `general` class (h = exp2(c * log2 d2)).
 //
-// The FP64 pipe is the bottleneck of every IDW kernel, so these are written for the fewest FP64-pipe
-// instructions that still give ~1e-15: table-driven argument reduction (tables live in shared memory, built once
-// per CTA), short series with coefficients in the constant bank, and all range reduction, special-case handling
-// and 2^n scaling on the integer pipe (no FP64 compares, no branches).
-//   tab_log2    : 8 FP64 + I2F + one 16-byte table load  (128 entries {1/c_i, -log2(1/c_i)}, degree-6 series)
-//   tab_exp2_32 : 11 FP64 + one 8-byte table load        (32 entries 2^(j/32), degree-6 series)
-// Both SATURATE instead of producing infinities from finite-range inputs (log2(0) = -2^1000-ish), which removes
-// every special case from the kernel: c*L is never inf, and 0*L == 0 gives exp2(0) == 1 exactly (Go: Pow(d,-0) == 1
-// even at d == 0).  Subnormal d2 is flushed to zero like rcp.approx.ftz does in the other classes.
-// History (c2 band, p = 1.7, G evals/s): libdevice log2()/exp2() 218; table-free FDLIBM-style versions (16 + 17
-// FP64 instructions) 302, then 367 once their coefficients sat in the constant bank and the per-cell branches
-// were gone; the table-driven versions here need 19 instead of 33.
+// Measured on B200 (scripts/ubench.cu, profiles/r2_ubench.txt): the FP64 pipe issues 64 lanes/clk/SM, and so does the
+// integer ALU pipe (LOP3 / SHF / IADD3) -- an integer instruction costs as much as a DFMA, I2F.F64 / F2I.F64 run at
+// 16 lanes/clk/SM and stall the FP64 pipe for about one DFMA slot.  The general class is therefore written for the
+// fewest FP64 *and* integer instructions per pair:
+//   * log2: 1024-entry table {1/c_i, -log2(1/c_i)} (16 KB of shared memory per CTA, copied from a per-device global
+//     image), |r| <= 2^-11, so a 3-coefficient series is enough (5e-15 absolute); the exponent is converted with the
+//     2^52 magic-number add instead of I2F;
+//   * exp2: 512-entry table 2^(j/512) (4 KB), 3-coefficient series (2.2e-15 relative); rounding to the nearest table
+//     point with the 1.5*2^52 magic number;
+//   * `fold` form for single-exponent passes: the multiplier c is folded into the log table and the series
+//     coefficients when the CTA loads them, so T = 512 c log2(d2) comes out of the log's own final FMA;
+//   * `single` scaling: when |c| <= 0.995 the result exponent stays normal for every positive normal d2, so 2^n is an
+//     integer add on the table value's exponent field instead of two multiplies.
+// FP64 instructions per pair: 6 (log2, +1 with the magic add) and 7 (exp2) against 8 + 11 in round 1.
+// Specials: the `any` forms SATURATE instead of producing infinities from finite-range inputs (log2(0) ~ -2^1000),
+// which removes every special case from the kernel: c*L is never inf, and 0*L == 0 gives exp2(0) == 1 exactly (Go:
+// Pow(d,-0) == 1 even at d == 0).  The `safe` forms (all exponents > 0) have no special handling at all: d2 == 0 /
+// subnormal cells are poisoned afterwards by idw_poison_kernel (idw_launch.cu).  Subnormal d2 counts as zero, like
+// rcp.approx.ftz does in the other classes.
 // __host__ versions exist only so tests/ can compile this header on the CPU and compare with libm.
 #pragma once
 #include <cuda_runtime.h>
@@ -27,16 +34,23 @@ namespace v2r {
 #else
 #define V2R_COEF static const
 #endif
-// log2(1+r) = r * (kLg[0] + kLg[1] r + ... + kLg[5] r^5),  kLg[k] = log2(e) * (-1)^k / (k+1);  |r| <= 2^-8
-V2R_COEF double kLg[6] = {1.4426950408889634074, -0.72134752044448170368, 0.48089834696298780245,
-                          -0.36067376022224085184, 0.28853900817779268147, -0.24044917348149390123};
-// 2^(g/32) = 1 + g * (kEx[0] + kEx[1] g + ... + kEx[5] g^5),  kEx[k] = (ln2/32)^(k+1) / (k+1)!;  |g| <= 1/2
-V2R_COEF double kEx[6] = {0.021660849392498290919, 0.00023459619820224678939, 1.6938509724371820054e-6,
-                          9.1725627018246432895e-9, 3.9737099845494161318e-11, 1.4345655584131935569e-13};
-V2R_COEF double kMagic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
+constexpr int kLogBits = 10, kExpBits = 9;
+constexpr int kLogTab = 1 << kLogBits, kExpTab = 1 << kExpBits;
+constexpr double kExpScale = (double)kExpTab;  // T = kExpScale * c * log2(d2)
 
-struct LogEntry { double inv_c, log2_c; };  // 1/c_i rounded to double, and -log2 of that rounded value
-constexpr int kLogTab = 128, kExpTab = 32;
+// log2(1+r) = r * (kLg[0] + kLg[1] r + kLg[2] r^2), |r| <= 2^-11 (1 + 2^-20): interpolated at the Chebyshev nodes,
+// maximum error 5.2e-15 in log2 units (scripts/fit_coefficients.py)
+V2R_COEF double kLg[3] = {1.4426950408889634074, -0.72134758493810647712, 0.48089839855788806054};
+// 2^(g/512) = 1 + g * (kEx[0] + kEx[1] g + kEx[2] g^2), |g| <= 1/2: maximum relative error 2.2e-15
+V2R_COEF double kEx[3] = {0.0013538030870311431825, 9.1639142547048926913e-7, 4.1353784217323216102e-10};
+V2R_COEF double kMagic = 6755399441055744.0;        // 1.5 * 2^52: adding it rounds to the nearest integer
+V2R_COEF double kMagicExp = 4503599627371519.0;     // 2^52 + 1023: make_double(0x43300000, e) - this == e - 1023
+
+struct LogEntry { double inv_c, log2_c; };  // 1/c rounded to double, and -log2 of that rounded value (or c times it: fold)
+struct GenTables {
+    LogEntry lg[kLogTab];
+    double ex[kExpTab];
+};
 
 __host__ __device__ __forceinline__ int hi_word(double a) {
 #ifdef __CUDA_ARCH__
@@ -59,81 +73,84 @@ __host__ __device__ __forceinline__ double make_double(int hi, int lo) {
     uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double a; memcpy(&a, &u, 8); return a;
 #endif
 }
-__host__ __device__ __forceinline__ double int2double(int k) {
-#ifdef __CUDA_ARCH__
-    return __int2double_rn(k);
-#else
-    return (double)k;
-#endif
-}
 
-// Entry i of the tables (the CTA builds them once, one entry per thread, before the point loop).
-// c_i is the midpoint of the i-th 1/128 slice of [1,2); log2_c is taken from the ROUNDED reciprocal, so
-// log2(m) = log2_c + log2(m * inv_c) holds exactly for the numbers actually used.
-__host__ __device__ inline void build_log_entry(int i, LogEntry &e) {
-    const double c = 1.0 + (i + 0.5) / kLogTab;
-    e.inv_c = 1.0 / c;
-    e.log2_c = -log2(e.inv_c);
-}
-__host__ __device__ inline double build_exp_entry(int j) { return exp2((double)j / kExpTab); }
-
-// log2(a) for a >= 0, SATURATING: a == 0 (or subnormal / negative) -> about -2^1000 (finite), +inf / NaN -> NaN.
-// POISON_ZERO (all exponents of the pass are > 0, where d2 = 0 makes the whole cell NaN anyway): zero, subnormal,
-// inf and NaN all give NaN, found with ONE unsigned range test.
-template <bool POISON_ZERO = false>
-__host__ __device__ __forceinline__ double tab_log2(double a, const LogEntry *tab) {
-    const int hi = hi_word(a);
-    const int k = (hi >> 20) - 1023;
-    const LogEntry t = tab[(hi >> 13) & (kLogTab - 1)];
-    const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(a));  // [1, 2)
-    const double r = fma(m, t.inv_c, -1.0);                                    // |r| <= 2^-8
-    double q = kLg[5];
-    q = fma(q, r, kLg[4]);
-    q = fma(q, r, kLg[3]);
-    q = fma(q, r, kLg[2]);
-    q = fma(q, r, kLg[1]);
-    q = fma(q, r, kLg[0]);
-    const double L = fma(q, r, int2double(k) + t.log2_c);
-    int lhi = hi_word(L);
-    if constexpr (POISON_ZERO) {
-        if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) lhi = 0x7ff80000;  // not a positive normal number: NaN
-    } else {
-        if (hi < 0x00100000) lhi = (int)0xfe700000;   // zero / subnormal / negative: huge negative, finite
-        if (hi >= 0x7ff00000) lhi = 0x7ff80000;       // +inf / NaN: NaN
+// Entry i of the tables.  c_i is the midpoint of the i-th 1/1024 slice of [1,2); log2_c is taken from the ROUNDED
+// reciprocal, so log2(m) = log2_c + log2(m * inv_c) holds exactly for the numbers actually used.  Built once per
+// device on the host (long double libm) and copied to global memory; every CTA copies the image to shared memory.
+inline void build_gen_tables(GenTables &t) {
+    for (int i = 0; i < kLogTab; ++i) {
+        const long double c = 1.0L + (i + 0.5L) / kLogTab;
+        t.lg[i].inv_c = (double)(1.0L / c);
+        t.lg[i].log2_c = (double)(-log2l((long double)t.lg[i].inv_c));
     }
+    for (int j = 0; j < kExpTab; ++j) t.ex[j] = (double)exp2l((long double)j / kExpTab);
+}
+
+// ---- log2 ------------------------------------------------------------------------------------------------
+// Core: no special handling.  a must be a positive normal double for the result to mean anything.
+// Returns  scale * log2(a)  where `scale` is 1 (plain table, lg = kLg) or 512 c (folded table: log2_c pre-multiplied,
+// lg = 512 c kLg[], kscale = 512 c).  6 FP64-pipe instructions + 1 DADD for the exponent, 5 integer.
+__host__ __device__ __forceinline__ double log2_core(double a, const LogEntry *tab, double lg0, double lg1, double lg2,
+                                                     double kscale) {
+    const int hi = hi_word(a);
+    const LogEntry t = tab[(hi >> (20 - kLogBits)) & (kLogTab - 1)];
+    const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(a));  // [1, 2)
+    const double r = fma(m, t.inv_c, -1.0);                                    // |r| <= 2^-11
+    const double kd = make_double(0x43300000, (int)((unsigned)hi >> 20)) - kMagicExp;  // unbiased exponent, exact
+    double q = fma(lg2, r, lg1);
+    q = fma(q, r, lg0);
+    return fma(q, r, fma(kd, kscale, t.log2_c));
+}
+
+// log2(a), SATURATING: a == 0 (or subnormal / negative) -> about -2^1000 (finite), +inf / NaN -> NaN.
+__host__ __device__ __forceinline__ double tab_log2_any(double a, const LogEntry *tab) {
+    const double L = log2_core(a, tab, kLg[0], kLg[1], kLg[2], 1.0);
+    const int hi = hi_word(a);
+    int lhi = hi_word(L);
+    if (hi < 0x00100000) lhi = (int)0xfe700000;   // zero / subnormal / negative: huge negative, finite
+    if (hi >= 0x7ff00000) lhi = 0x7ff80000;       // +inf / NaN: NaN
     return make_double(lhi, lo_word(L));
 }
+// log2(a) for positive normal a (the `safe` passes): no special handling.
+__host__ __device__ __forceinline__ double tab_log2_safe(double a, const LogEntry *tab) {
+    return log2_core(a, tab, kLg[0], kLg[1], kLg[2], 1.0);
+}
 
-// 2^(T/32) for finite T (any magnitude) or NaN; the caller folds the factor 32 into its multiplier.
-// Saturates: T/32 >= 1024 -> +inf, T/32 <= -1075 -> 0.
-// BOUNDED: the caller guarantees |T/32| < 2040 or NaN (true when |p| <= 3.75: |log2 d2| <= 1075 for every positive
-// normal d2, and poisoned logs are NaN), so the clamp is skipped.
-template <bool BOUNDED = false>
-__host__ __device__ __forceinline__ double tab_exp2_32(double T, const double *tab) {
+// ---- exp2 ------------------------------------------------------------------------------------------------
+// 2^(T/512).  Scaling of the result by 2^n:
+//   EXP_ANY     any finite T or NaN: |T/512| >= 2040 is clamped, 2^n in two factors so overflow saturates to +inf and
+//               underflow rounds through the subnormals to 0 by the multiplies themselves;
+//   EXP_BOUNDED the caller guarantees |T/512| < 2040 (or NaN): no clamp, two factors;
+//   EXP_SINGLE  the caller guarantees |T/512| <= 1021: n is added to the table value's exponent field (integer add).
+enum ExpMode : int { EXP_ANY = 0, EXP_BOUNDED = 1, EXP_SINGLE = 2 };
+
+template <int XM>
+__host__ __device__ __forceinline__ double tab_exp2(double T, const double *tab) {
     double Tc = T;
-    if constexpr (!BOUNDED) {
-        // clamp 65280 <= |T| < inf (i.e. |T/32| >= 2040) to +-65280 with one unsigned range test; NaN passes through
+    if constexpr (XM == EXP_ANY) {
+        // clamp 2040*512 <= |T| < inf to +-2040*512 with one unsigned range test; NaN passes through
         const int hi = hi_word(T);
-        const bool big = (unsigned)((hi & 0x7fffffff) - 0x40efe000) < (unsigned)(0x7ff00000 - 0x40efe000);
-        Tc = make_double(big ? ((hi & (int)0x80000000) | 0x40efe000) : hi, big ? 0 : lo_word(T));
+        constexpr int kLim = 0x412fe000;  // high word of 2040 * 512 = 1044480.0
+        const bool big = (unsigned)((hi & 0x7fffffff) - kLim) < (unsigned)(0x7ff00000 - kLim);
+        Tc = make_double(big ? ((hi & (int)0x80000000) | kLim) : hi, big ? 0 : lo_word(T));
     }
     const double Tn = Tc + kMagic;
     const int N = lo_word(Tn);                // nearest integer to T (two's complement in the low word)
     const double g = Tc - (Tn - kMagic);      // in [-1/2, 1/2], exact
-    double p = kEx[5];
-    p = fma(p, g, kEx[4]);
-    p = fma(p, g, kEx[3]);
-    p = fma(p, g, kEx[2]);
-    p = fma(p, g, kEx[1]);
-    p = fma(p, g, kEx[0]);
-    p = fma(p, g, 1.0);                       // 2^(g/32)
-    const double e = tab[N & (kExpTab - 1)];  // 2^(j/32) in [1, 2)
-    const int n = N >> 5;                     // floor(N / 32), |n| <= 2040
-    const int n1 = n >> 1, n2 = n - n1;
-    // 2^n in two factors, so overflow saturates to +inf and underflow rounds through the subnormals to 0 by the
-    // multiplies themselves; the first factor rides on the table value's exponent field (an integer add)
-    const double s1 = make_double(hi_word(e) + (n1 << 20), lo_word(e));
-    return (p * s1) * make_double((n2 + 1023) << 20, 0);
+    double q = fma(kEx[2], g, kEx[1]);
+    q = fma(q, g, kEx[0]);
+    const double p = fma(q, g, 1.0);          // 2^(g/512)
+    const double e = tab[N & (kExpTab - 1)];  // 2^(j/512) in [1, 2)
+    if constexpr (XM == EXP_SINGLE) {
+        // floor(N / 512) << 20, added to the exponent field of e
+        const double s = make_double(hi_word(e) + (int)(((unsigned)N << (20 - kExpBits)) & 0xfff00000u), lo_word(e));
+        return p * s;
+    } else {
+        const int n = N >> kExpBits;          // floor(N / 512), |n| <= 2040
+        const int n1 = n >> 1, n2 = n - n1;
+        const double s1 = make_double(hi_word(e) + (n1 << 20), lo_word(e));
+        return (p * s1) * make_double((n2 + 1023) << 20, 0);
+    }
 }
 
 // MUFU.RCP64H / MUFU.RSQ64H: ~2^-20 relative seeds computed from the high word of the operand.
