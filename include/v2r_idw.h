@@ -150,8 +150,9 @@ int v2r_idw_launch_rows(int device, void *stream, const double *d_x, const doubl
                         int n_exps, int precision, double *d_out);
 
 /* ---- measurement ------------------------------------------------------------------------ */
-/* Timing of the most recent solve on this context (CUDA events, milliseconds): host->device,
- * kernels (max over the context's devices), gather + device->host.  Any pointer may be NULL. */
+/* Timing of the most recent solve on this context (CUDA events, milliseconds; max over the context's devices):
+ * host->device upload + broadcast; span of the kernels (first launch to last completion); copy-out (gather +
+ * device->host) that was NOT hidden behind kernels, i.e. last kernel end to last copy end.  Any pointer may be NULL. */
 int v2r_idw_last_timing(v2r_idw_ctx *ctx, double *h2d_ms, double *kernel_ms, double *d2h_ms);
 /* Number of kernel launches issued by this library since it was loaded (all contexts). */
 int64_t v2r_idw_launch_count(void);

@@ -286,9 +286,24 @@ int64_t oracle_make_coord_space(int64_t n, const double *x, const double *y, con
  * px = xMin + float64(c)*xStep (separate multiply and add).  Exact-hit test is the key lookup
  * (:13-16), not a distance test.  The reference iterates the Go map in random order; the oracle
  * sums in array order. */
+/* mode 0: array order (the oracle's fixed choice).  mode 1: REVERSE array order -- another valid execution of the
+ * reference, whose `range` over the Go map visits the points in a random order every time.  mode 2: the reference's
+ * own float64 terms (same DistExp, same w*h product) accumulated in 80-bit long double: the order-independent value
+ * that every execution of the reference scatters around by its float64 summation error. */
+static double cell_idw_mode(const keymap *m_const, int64_t n, const double *x, const double *y,
+                            const double *w, double x_min, double x_step, double y_min, double y_step,
+                            double exp, int64_t r, int64_t c, int mode);
+
 static double cell_idw(const keymap *m_const, int64_t n, const double *x, const double *y,
                        const double *w, double x_min, double x_step, double y_min, double y_step,
                        double exp, int64_t r, int64_t c)
+{
+    return cell_idw_mode(m_const, n, x, y, w, x_min, x_step, y_min, y_step, exp, r, c, 0);
+}
+
+static double cell_idw_mode(const keymap *m_const, int64_t n, const double *x, const double *y,
+                            const double *w, double x_min, double x_step, double y_min, double y_step,
+                            double exp, int64_t r, int64_t c, int mode)
 {
     keymap *m = (keymap *)m_const;
     double px = x_min + (double)c * x_step;
@@ -299,8 +314,18 @@ static double cell_idw(const keymap *m_const, int64_t n, const double *x, const 
         if (m->kr[i] == r && m->kc[i] == c) return w[m->slot[i]];
         i = (i + 1) & m->mask;
     }
+    if (mode == 2) {
+        long double num = 0.0L, den = 0.0L;
+        for (int64_t k = 0; k < n; k++) {
+            double h = oracle_dist_exp(px, py, x[k], y[k], exp);
+            num += (long double)(w[k] * h);
+            den += (long double)h;
+        }
+        return (double)(num / den);
+    }
     double num = 0.0, den = 0.0;
-    for (int64_t k = 0; k < n; k++) {
+    for (int64_t q = 0; q < n; q++) {
+        int64_t k = mode == 1 ? n - 1 - q : q;
         double h = oracle_dist_exp(px, py, x[k], y[k], exp);
         num += w[k] * h;
         den += h;
@@ -339,22 +364,37 @@ int oracle_solve_rows(int64_t n, const double *x, const double *y, const double 
  * the CPU.  nthreads > 1 splits the list statically. */
 typedef struct {
     const keymap *m; int64_t n; const double *x, *y, *w; double x_min, x_step, y_min, y_step, exp;
-    const int64_t *rr, *cc; int64_t lo, hi; double *out;
+    const int64_t *rr, *cc;
+    int mode; int64_t lo, hi; double *out;
 } cells_job;
 
 static void *cells_worker(void *arg)
 {
     cells_job *j = (cells_job *)arg;
     for (int64_t i = j->lo; i < j->hi; i++)
-        j->out[i] = cell_idw(j->m, j->n, j->x, j->y, j->w, j->x_min, j->x_step, j->y_min, j->y_step, j->exp,
-                             j->rr[i], j->cc[i]);
+        j->out[i] = cell_idw_mode(j->m, j->n, j->x, j->y, j->w, j->x_min, j->x_step, j->y_min, j->y_step, j->exp,
+                                  j->rr[i], j->cc[i], j->mode);
     return NULL;
 }
+
+int oracle_solve_cells_mode(int64_t n, const double *x, const double *y, const double *w,
+                            const int64_t *kr, const int64_t *kc, double x_min, double x_step,
+                            double y_min, double y_step, int64_t ncells, const int64_t *rr,
+                            const int64_t *cc, double exp, int nthreads, int mode, double *out);
 
 int oracle_solve_cells(int64_t n, const double *x, const double *y, const double *w,
                        const int64_t *kr, const int64_t *kc, double x_min, double x_step,
                        double y_min, double y_step, int64_t ncells, const int64_t *rr,
                        const int64_t *cc, double exp, int nthreads, double *out)
+{
+    return oracle_solve_cells_mode(n, x, y, w, kr, kc, x_min, x_step, y_min, y_step, ncells, rr, cc, exp, nthreads, 0, out);
+}
+
+/* mode: 0 = array order, 1 = reverse order, 2 = the reference's float64 terms summed in long double (cell_idw_mode) */
+int oracle_solve_cells_mode(int64_t n, const double *x, const double *y, const double *w,
+                            const int64_t *kr, const int64_t *kc, double x_min, double x_step,
+                            double y_min, double y_step, int64_t ncells, const int64_t *rr,
+                            const int64_t *cc, double exp, int nthreads, int mode, double *out)
 {
     keymap m;
     if (build_keymap(&m, n, kr, kc) != 0) return -1;
@@ -364,7 +404,7 @@ int oracle_solve_cells(int64_t n, const double *x, const double *y, const double
     pthread_t th[256];
     int started = 0;
     for (int t = 0; t < nthreads; t++) {
-        cells_job j = {&m, n, x, y, w, x_min, x_step, y_min, y_step, exp, rr, cc,
+        cells_job j = {&m, n, x, y, w, x_min, x_step, y_min, y_step, exp, rr, cc, mode,
                        ncells * t / nthreads, ncells * (t + 1) / nthreads, out};
         jobs[t] = j;
     }

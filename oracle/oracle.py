@@ -69,6 +69,8 @@ def lib():
         L.oracle_full_solve_ld.argtypes = pts + geo + [C.c_int64, C.c_int64, C.c_double, _D, _D]
         L.oracle_solve_cells.restype = C.c_int
         L.oracle_solve_cells.argtypes = pts + geo + [C.c_int64, _I, _I, C.c_double, C.c_int, _D]
+        L.oracle_solve_cells_mode.restype = C.c_int
+        L.oracle_solve_cells_mode.argtypes = pts + geo + [C.c_int64, _I, _I, C.c_double, C.c_int, C.c_int, _D]
         L.oracle_exp_range.restype = C.c_int64
         L.oracle_exp_range.argtypes = [C.c_double] * 3 + [_D, C.c_int64]
         L.oracle_num_threads.restype = C.c_int
@@ -189,12 +191,18 @@ def chunk_solve_rows(ps: PointSet, xinfo: Info, yinfo: Info, rows: int, cols: in
     return out
 
 
-def solve_cells(ps: PointSet, xinfo: Info, yinfo: Info, exp: float, rr, cc, nthreads: int = 0):
-    """calculateIDW on a list of cells (for spot checks of full-size rasters)."""
+ORDER_INPUT, ORDER_REVERSE, SUM_LONG_DOUBLE = 0, 1, 2
+
+
+def solve_cells(ps: PointSet, xinfo: Info, yinfo: Info, exp: float, rr, cc, nthreads: int = 0, mode: int = ORDER_INPUT):
+    """calculateIDW on a list of cells (for spot checks of full-size rasters).  mode: ORDER_INPUT = points in array
+    order (the oracle's fixed choice); ORDER_REVERSE = the same float64 arithmetic in reverse order -- another valid
+    execution of the reference, whose Go map iteration is randomised per `range`; SUM_LONG_DOUBLE = the reference's
+    float64 terms summed in 80-bit long double, the order-independent value its executions scatter around."""
     rr, cc = _i64(rr), _i64(cc)
     out = np.empty(len(rr))
     keep, a = _args(ps, xinfo, yinfo)
-    rc = lib().oracle_solve_cells(*a, len(rr), _i(rr), _i(cc), exp, nthreads or num_threads(), _d(out))
+    rc = lib().oracle_solve_cells_mode(*a, len(rr), _i(rr), _i(cc), exp, nthreads or num_threads(), mode, _d(out))
     assert rc == 0
     return out
 
@@ -257,7 +265,7 @@ def read_geopackage(path: str, layer: str, field: str, step_x: float, step_y: fl
         geom_col, srs_id = con.execute(
             "select column_name, srs_id from gpkg_geometry_columns where table_name=?", (layer,)).fetchone()
         proj = con.execute("select definition from gpkg_spatial_ref_sys where srs_id=?", (srs_id,)).fetchone()[0]
-        rows = con.execute(f'select "{geom_col}", "{field}" from "{layer}" order by fid').fetchall()
+        rows = con.execute(f'select "{geom_col}", "{field}" from "{layer}" order by rowid').fetchall()
     finally:
         con.close()
     xs, ys, ws = [], [], []

@@ -152,3 +152,20 @@ def test_cpp_readers_parse_bit_exactly_and_dedupe_like_the_oracle(tmp_path):
     g = json.loads(run("idw", "-g", "-f", os.path.join(GOLDEN, "input.gpkg"), "--layer", "wsels", "--field", "elevation", "--sx", "1",
                        "--sy", "2", "--plan", "-e", "--dump-points", "14").stdout)
     assert g["raw"] == exp["points"]
+
+
+def test_gpkg_with_a_primary_key_that_is_not_called_fid(tmp_path):
+    """The reference reads through OGR (l.Feature(1..count), io_gdal.go:180-190), which works whatever the FID column
+    is called; the SQL readers order by rowid (an INTEGER PRIMARY KEY is an alias of it), not by a column named fid."""
+    from v2r_b200 import read_data
+    rng = np.random.default_rng(12)
+    x, y, w = rng.uniform(0, 900, 50), rng.uniform(0, 400, 50), rng.normal(0, 10, 50)
+    f = str(tmp_path / "objectid.gpkg")
+    workloads.write_gpkg(f, x, y, w, pk="OBJECTID")
+    x2, y2, w2, _, _, _ = read_data.ReadGeoPackage(f, "wsels", "elevation", 10.0, 10.0)
+    assert np.array_equal(x, x2) and np.array_equal(y, y2) and np.array_equal(w, w2)
+    x3, y3, w3 = O.read_geopackage(f, "wsels", "elevation", 10.0, 10.0)[:3]
+    assert np.array_equal(x, x3) and np.array_equal(w, w3)
+    g = json.loads(run("idw", "-g", "-f", f, "--layer", "wsels", "--field", "elevation", "--sx", "10", "--sy", "10", "--plan", "-e",
+                       "--dump-points", "50").stdout)
+    assert g["raw"] == [[float(a), float(b), float(c)] for a, b, c in zip(x, y, w)]

@@ -1,6 +1,8 @@
 """Multi-GPU parity (needs >= 2 B200s; skipped otherwise): the single-process context of the Go host
-(v2r_idw_init(N): NCCL broadcast of the points, row bands, NCCL gather to device 0) must return exactly
-the raster of a single-GPU solve -- every cell is computed by the same kernel on the same inputs."""
+(v2r_idw_init(N): NCCL broadcast of the points, row bands, copy-out either straight from every device into a pinned
+host raster or by an NCCL gather to device 0 for a pageable one) must return exactly the raster of a single-GPU
+solve -- every cell is computed by the same kernel on the same inputs, and a cell's sums are defined over point
+segments, not over the way the launch was cut."""
 import numpy as np
 import pytest
 
@@ -28,8 +30,18 @@ def test_single_process_multi_gpu_equals_single_gpu(n_gpus):
         want = c1.solve(ps, grid, exps)
         want32 = c1.solve(ps, grid, [2.0], _lib.FP32)
     with V.IdwContext(n_gpus) as cn:
-        got = cn.solve(ps, grid, exps)
+        got = cn.solve(ps, grid, exps)                               # pageable raster: NCCL gather path
         assert np.array_equal(got, want)
+        pinned = V.PinnedArray(want.shape)                           # page-locked raster: every device copies its own band
+        try:
+            cn.solve(ps, grid, exps, out=pinned.array)
+            assert np.array_equal(pinned.array, want)
+            pinned.array[:] = 0
+            for r0, band in cn.stream(ps, grid, exps, band_rows=48, pinned=True):
+                pinned.array[:, r0:r0 + band.shape[1]] = band
+            assert np.array_equal(pinned.array, want)
+        finally:
+            pinned.free()
         assert np.array_equal(cn.solve(ps, grid, [2.0], _lib.FP32), want32)
         parts = np.full_like(want, np.nan)
         for r0, band in cn.stream(ps, grid, exps, band_rows=64):     # bands arrive device by device

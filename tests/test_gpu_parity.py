@@ -59,6 +59,23 @@ def assert_parity(z, z_ref, scale, rel=REL, what=""):
     return float(err.max()) if err.size else 0.0
 
 
+def assert_parity_cells(got, ps, xi, yi, p, rr, cc, scale_ps=None, rel=REL, what=""):
+    """Sampled cells of a full-size raster.  With 1e5..2e6 points the reference's OWN result depends on the order in
+    which its Go map happens to be iterated by more than 1e-12 for large exponents (c3, p = 4.5: input order and
+    reverse order, two valid executions, differ by 1.9e-12): once the running sum is large, thousands of tiny terms
+    are rounded away.  So the check is made against the order-independent value -- the reference's float64 terms
+    (same DistExp, same w*h) summed in long double -- at 1e-12, and against the oracle's input-order execution with
+    that execution's own distance from the exact sum as allowance."""
+    exact = O.solve_cells(o_ps(ps), o_info(xi), o_info(yi), float(p), rr, cc, mode=O.SUM_LONG_DOUBLE)
+    seq = O.solve_cells(o_ps(ps), o_info(xi), o_info(yi), float(p), rr, cc)
+    scale = np.abs(exact) if scale_ps is None else O.solve_cells(o_ps(scale_ps), o_info(xi), o_info(yi), float(p), rr, cc)
+    err = assert_parity(got, exact, scale, rel=rel, what=what + " vs exact sum of the reference's terms")
+    ok = ~np.isnan(seq)
+    s = np.maximum(np.maximum(np.abs(seq[ok]), scale[ok]), 1e-300)
+    assert np.all(np.abs(np.asarray(got)[ok] - seq[ok]) / s <= rel + np.abs(seq[ok] - exact[ok]) / s), f"{what}: vs input-order oracle"
+    return err
+
+
 def random_case(seed, n, rows, cols, step=1.0, x0=0.0, y0=0.0, signed=True):
     rng = np.random.default_rng(seed)
     xi = V.Info(x0, x0 + cols * step - 1, step)
@@ -243,7 +260,7 @@ def c2():
 
 def test_c2_full_size_spot_check_and_properties(ctx, c2):
     """BASELINE.json config 2 (100 k points -> 4096^2, p = 2) at full size:
-    (a) 400 random cells + every 997th exact-hit cell against the oracle,
+    (a) 5000 random cells, the four corners and every 97th exact-hit cell against the oracle,
     (b) constant weights reproduce the constant, (c) linearity in the weights,
     (d) row bands computed separately are bit-identical to the full raster."""
     ps, xi, yi, exps = c2
@@ -252,12 +269,9 @@ def test_c2_full_size_spot_check_and_properties(ctx, c2):
     z = ctx.solve(ps, grid, exps)[0]
     assert not np.isnan(z).any()
     rng = np.random.default_rng(3)
-    rr = np.concatenate([rng.integers(0, grid.rows, 400), ps.key_r[::997]])
-    cc = np.concatenate([rng.integers(0, grid.cols, 400), ps.key_c[::997]])
-    ref = O.solve_cells(o_ps(ps), o_info(xi), o_info(yi), 2.0, rr, cc)
-    ops_abs = O.PointSet(ps.x, ps.y, np.abs(ps.w), ps.key_r, ps.key_c)
-    scale = O.solve_cells(ops_abs, o_info(xi), o_info(yi), 2.0, rr, cc)
-    assert_parity(z[rr, cc], ref, scale, what="c2 spot check")
+    rr = np.concatenate([rng.integers(0, grid.rows, 5000), ps.key_r[::97], [0, 0, grid.rows - 1, grid.rows - 1]])
+    cc = np.concatenate([rng.integers(0, grid.cols, 5000), ps.key_c[::97], [0, grid.cols - 1, 0, grid.cols - 1]])
+    assert_parity_cells(z[rr, cc], ps, xi, yi, 2.0, rr, cc, what="c2 spot check")
     assert np.array_equal(z[ps.key_r, ps.key_c], ps.w)           # all 99.7 k exact-hit cells bit-equal
     # (b) constant field
     const = V.PointSet(ps.x, ps.y, np.full(len(ps), 123.456), ps.key_r, ps.key_c)
@@ -275,19 +289,19 @@ def test_c2_full_size_spot_check_and_properties(ctx, c2):
 
 
 def test_c3_sweep_full_width_band(ctx):
-    """BASELINE.json config 3 (250 k points -> 8192^2, p = 0.5..4.5, one pass): one 32-row band of the
-    full-width grid against the oracle on sampled cells, all nine exponents."""
+    """BASELINE.json config 3 (250 k points -> 8192^2, p = 0.5..4.5, one pass): three 32-row bands of the
+    full-width grid (first, middle, last rows) against the oracle on 510 sampled cells, all nine exponents."""
     x, y, w, xi, yi, exps = workloads.make("c3")
     ps = V.MakeCoordSpace(x, y, w, xi, yi)
     grid = make_grid(xi, yi)
     assert (grid.rows, grid.cols, len(exps)) == (8192, 8192, 9)
-    r0 = 4096
-    z = ctx.solve_rows(ps, grid, r0, 32, exps)
     rng = np.random.default_rng(5)
-    rr, cc = r0 + rng.integers(0, 32, 40), rng.integers(0, grid.cols, 40)
-    for e, p in enumerate(exps):
-        ref = O.solve_cells(o_ps(ps), o_info(xi), o_info(yi), float(p), rr, cc)
-        assert_parity(z[e][rr - r0, cc], ref, np.abs(ref), what=f"c3 p={p}")   # w >= 0 so scale == |z|
+    for r0 in (0, 4096, grid.rows - 32):                                       # first rows, middle, last rows
+        z = ctx.solve_rows(ps, grid, r0, 32, exps)
+        rr, cc = r0 + rng.integers(0, 32, 170), rng.integers(0, grid.cols, 170)
+        rr[:2], cc[:2] = (r0, r0 + 31), (0, grid.cols - 1)
+        for e, p in enumerate(exps):                                           # 510 cells x 9 exponents
+            assert_parity_cells(z[e][rr - r0, cc], ps, xi, yi, p, rr, cc, what=f"c3 rows {r0} p={p}")   # w >= 0: scale == |z|
 
 
 # --------------------------------------------------------------------------- FP32 fast path
@@ -340,40 +354,55 @@ def test_fp32_c2_full_size_spot_check(ctx, c2):
 
 # --------------------------------------------------------------------------- c4 / c5 shapes, randomized sweep
 def test_c4_clustered_full_width_band(ctx):
-    """BASELINE.json config 4 (1 M clustered points -> 16384^2, p = 2): a 32-row full-width band through the
-    paired-reciprocal kernel and the FP32 path, spot-checked against the oracle; dedupe merges clustered points."""
+    """BASELINE.json config 4 (1 M clustered points -> 16384^2, p = 2): five 32-row full-width bands (first
+    to last rows, 2100 cells) through the paired-reciprocal kernel and the FP32 path against the oracle, then a pass
+    with signed weights; dedupe merges clustered points."""
     x, y, w, xi, yi, exps = workloads.make("c4")
     ps = V.MakeCoordSpace(x, y, w, xi, yi)
     ops = O.make_coord_space(x, y, w, o_info(xi), o_info(yi))
     assert len(ps) == len(ops) < len(x) and np.array_equal(ps.w, ops.w) and np.array_equal(ps.key_c, ops.key_c)
     grid = make_grid(xi, yi)
     assert (grid.rows, grid.cols) == (16384, 16384)
-    r0 = 8192
-    z = ctx.solve_rows(ps, grid, r0, 32, exps)[0]
-    z32 = ctx.solve_rows(ps, grid, r0, 32, exps, _lib.FP32)[0]
     rng = np.random.default_rng(8)
-    rr, cc = r0 + rng.integers(0, 32, 48), rng.integers(0, grid.cols, 48)
-    ref = O.solve_cells(ops, o_info(xi), o_info(yi), 2.0, rr, cc)
-    assert_parity(z[rr - r0, cc], ref, np.abs(ref), what="c4 band")
-    assert_parity(z32[rr - r0, cc], ref, np.abs(ref), rel=REL32, what="c4 band fp32")
-    inband = (ps.key_r >= r0) & (ps.key_r < r0 + 32)
-    assert inband.sum() > 0 and np.array_equal(z[ps.key_r[inband] - r0, ps.key_c[inband]], ps.w[inband])
+    bands = (0, 5000, 8192, 12345, grid.rows - 32)                             # first rows ... last rows, 5 x 420 cells
+    cells = {}
+    for r0 in bands:
+        z = ctx.solve_rows(ps, grid, r0, 32, exps)[0]
+        z32 = ctx.solve_rows(ps, grid, r0, 32, exps, _lib.FP32)[0]
+        rr, cc = r0 + rng.integers(0, 32, 420), rng.integers(0, grid.cols, 420)
+        rr[:2], cc[:2] = (r0, r0 + 31), (0, grid.cols - 1)
+        assert_parity_cells(z[rr - r0, cc], ps, xi, yi, 2.0, rr, cc, what=f"c4 rows {r0}")
+        ref = O.solve_cells(ops, o_info(xi), o_info(yi), 2.0, rr, cc)
+        err32 = assert_parity(z32[rr - r0, cc], ref, np.abs(ref), rel=REL32, what=f"c4 rows {r0} fp32")
+        assert err32 > 1e-12
+        inband = (ps.key_r >= r0) & (ps.key_r < r0 + 32)
+        assert inband.sum() > 0 and np.array_equal(z[ps.key_r[inband] - r0, ps.key_c[inband]], ps.w[inband])
+        assert np.array_equal(z32[ps.key_r[inband] - r0, ps.key_c[inband]], ps.w[inband])
+        cells[r0] = (rr, cc)
+    # second pass with SIGNED weights (the cancellation-robust tolerance at full size): w - 250 changes sign across the field
+    sg = V.PointSet(ps.x, ps.y, ps.w - 250.0, ps.key_r, ps.key_c)
+    ab = V.PointSet(ps.x, ps.y, np.abs(ps.w - 250.0), ps.key_r, ps.key_c)
+    for r0 in (bands[0], bands[2], bands[4]):
+        rr, cc = cells[r0]
+        z = ctx.solve_rows(sg, grid, r0, 32, exps)[0]
+        assert (z > 0).any() and (z < 0).any()
+        assert_parity_cells(z[rr - r0, cc], sg, xi, yi, 2.0, rr, cc, scale_ps=ab, what=f"c4 signed rows {r0}")
 
 
 def test_c5_epsg2284_sweep_band(ctx):
-    """BASELINE.json config 5 shape (EPSG:2284 offsets 1.1e7 / 3e6, 32768 columns, p = 1, 1.5, 2, 2.5) with
-    200 k of its points: a 16-row full-width band, all four exponents from one pass."""
-    x, y, w, xi, yi, exps = workloads.make("c5", n_points=200_000)
+    """BASELINE.json config 5 (EPSG:2284 offsets 1.1e7 / 3e6, all 2 M points, 32768 columns, p = 1, 1.5, 2, 2.5):
+    three 16-row full-width bands (first, middle, last rows), 210 cells x 4 exponents from one pass."""
+    x, y, w, xi, yi, exps = workloads.make("c5")
     ps = V.MakeCoordSpace(x, y, w, xi, yi)
     grid = make_grid(xi, yi)
-    assert (grid.rows, grid.cols) == (32768, 32768) and exps.tolist() == [1.0, 1.5, 2.0, 2.5]
-    r0 = 20000
-    z = ctx.solve_rows(ps, grid, r0, 16, exps)
+    assert (grid.rows, grid.cols) == (32768, 32768) and exps.tolist() == [1.0, 1.5, 2.0, 2.5] and len(ps) > 1_800_000
     rng = np.random.default_rng(9)
-    rr, cc = r0 + rng.integers(0, 16, 32), rng.integers(0, grid.cols, 32)
-    for e, p in enumerate(exps):
-        ref = O.solve_cells(o_ps(ps), o_info(xi), o_info(yi), float(p), rr, cc)
-        assert_parity(z[e][rr - r0, cc], ref, np.abs(ref), what=f"c5 p={p}")
+    for r0 in (0, 20000, grid.rows - 16):
+        z = ctx.solve_rows(ps, grid, r0, 16, exps)
+        rr, cc = r0 + rng.integers(0, 16, 70), rng.integers(0, grid.cols, 70)
+        rr[:2], cc[:2] = (r0, r0 + 15), (0, grid.cols - 1)
+        for e, p in enumerate(exps):
+            assert_parity_cells(z[e][rr - r0, cc], ps, xi, yi, p, rr, cc, what=f"c5 rows {r0} p={p}")
 
 
 def test_randomized_grids_points_and_sweeps(ctx):
@@ -458,3 +487,121 @@ def test_callable_from_many_threads(ctx):
     assert not errs, errs
     for i in range(len(exps)):
         assert np.array_equal(got[i], want[i]), exps[i]
+
+
+# --------------------------------------------------------------------------- boundary hardening (round 2)
+def test_stream_begin_has_read_the_points_when_it_returns(ctx):
+    """include/v2r_idw.h: the library never keeps a caller pointer after the call returns.  With PINNED point arrays
+    the upload is a truly asynchronous DMA, so _stream_begin must wait for it: the arrays are overwritten right after
+    the call and the rasters must still be those of the original points."""
+    import ctypes as C
+    L = _lib.load()
+    rng = np.random.default_rng(91)
+    xi, yi = V.Info(0, 95, 1.0), V.Info(0, 63, 1.0)
+    n = 300_000                                                       # 2.4 MB per array: the DMA takes a while
+    ps = _stale(rng.uniform(0, 96, n), rng.uniform(0, 64, n), rng.uniform(-5, 5, n))
+    grid = make_grid(xi, yi)
+    exps = np.array([2.0, 1.5])
+    want = ctx.solve(ps, grid, exps)
+    pins = [V.PinnedArray(len(ps), np.float64 if i < 3 else np.int64) for i in range(5)]
+    try:
+        for buf, src in zip(pins, (ps.x, ps.y, ps.w, ps.key_r, ps.key_c)):
+            buf.array[:] = src
+        args = [ctx._h] + [C.c_void_p(b.array.ctypes.data) for b in pins] + [len(ps), C.byref(grid), C.c_void_p(exps.ctypes.data), 2, 0, 0]
+        assert L.v2r_idw_stream_begin(*args) == _lib.OK
+        for b in pins[:3]:
+            b.array[:] = np.nan                                        # a reader reusing its buffers for the next file
+        pins[3].array[:] = 0
+        pins[4].array[:] = 0
+        got = np.empty_like(want)
+        buf = np.empty(want.size)
+        r0, nr = C.c_int64(), C.c_int64()
+        while True:
+            assert L.v2r_idw_stream_next(ctx._h, C.c_void_p(buf.ctypes.data), C.byref(r0), C.byref(nr)) == _lib.OK
+            if nr.value == 0:
+                break
+            got[:, r0.value:r0.value + nr.value] = buf[:2 * nr.value * grid.cols].reshape(2, nr.value, grid.cols)
+        assert L.v2r_idw_stream_end(ctx._h) == _lib.OK
+    finally:
+        for b in pins:
+            b.free()
+    assert np.array_equal(got, want)
+
+
+def _stale(x, y, w):
+    """points keyed far outside the grid: every cell goes through the sums (no exact hit)"""
+    n = len(x)
+    return V.PointSet(np.asarray(x, float), np.asarray(y, float), np.asarray(w, float), np.full(n, 10**9, np.int64), np.arange(n, dtype=np.int64))
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_paired_kernels_leave_no_hole_in_their_domain(ctx, prec):
+    """The paired p = 2 kernels need the product of two squared distances to stay a normal number.  Point tiles for
+    which that cannot be guaranteed on a CTA's cells run through the one-reciprocal loop: squared distances down to
+    1e-160 and up to 1e+160 (FP64; FP32: beyond 2^-60 / 2^58 cells^2) give the reference's finite values, exactly like
+    ordinary distances do."""
+    xi, yi = V.Info(0, 199, 1.0), V.Info(0, 99, 1.0)
+    rng = np.random.default_rng(17)
+    n = 1500
+    x, y, w = rng.uniform(0, 200, n), rng.uniform(0, 100, n), rng.uniform(1, 9, n)
+    if prec == "fp64":
+        tiny, far = 1e-80, 1e80
+        precision, rel = _lib.FP64, REL
+    else:
+        tiny, far = 1e-12, 1e12
+        precision, rel = _lib.FP32, REL32
+    # (a) points a hair off a node in BOTH axes (d2 = 2 tiny^2): a*b underflows; (b) points absurdly far away
+    #     (d2 ~ far^2): a*b overflows; (c) both in one 512-point tile together with ordinary points
+    x[3], y[3] = 17.0 + 17.0 * 2**-52, 40.0 + 40.0 * 2**-52          # one ulp off node (40, 17): d2 ~ 1e-29
+    x[700], y[700], w[700] = tiny, tiny, 123.0                        # a hair off node (0, 0), FP64: d2 = 2e-160
+    x[701], y[701] = far, -far
+    x[1400], y[1400] = -far, 3.0
+    ps = _stale(x, y, w)
+    z = V.solve(ps, xi, yi, [2.0], precision=precision, ctx=ctx)[0]
+    ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), 2.0)
+    assert np.isfinite(ref).all() and abs(ref[0, 0] - 123.0) < 1e-12  # that weight dominates its node completely
+    assert_parity(z, ref, ref, rel=rel, what=f"paired domain {prec}")
+    assert abs(z[0, 0] - 123.0) < (1e-12 if prec == "fp64" else 1e-3)
+
+
+def test_nan_coordinate_and_coincident_point_without_in_loop_specials(ctx):
+    """The general class with positive exponents and the packed FP32 kernel have no special cases in their loops:
+    a non-key cell that coincides with a point (reference: Pow(0, -p) = +Inf, Inf/Inf = NaN) and a NaN coordinate
+    (reference: every weight NaN) are handled by the poison pass -- same rasters as the oracle, NaN for NaN."""
+    xi, yi = V.Info(0, 63, 1.0), V.Info(0, 47, 1.0)
+    rng = np.random.default_rng(23)
+    n = 700
+    x, y, w = rng.uniform(0, 64, n), rng.uniform(0, 48, n), rng.uniform(1, 9, n)
+    x[10], y[10] = 20.0, 30.0                                         # exactly on node (30, 20), keyed elsewhere
+    x[600], y[600] = 63.0, 0.0
+    ps = _stale(x, y, w)
+    for p, precision, rel in ((1.7, _lib.FP64, REL), (0.3, _lib.FP64, REL), (2.2, _lib.FP64, REL), (2.0, _lib.FP32, REL32)):
+        z = V.solve(ps, xi, yi, [p], precision=precision, ctx=ctx)[0]
+        ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), p)
+        assert np.isnan(ref[30, 20]) and np.isnan(ref[0, 63]) and np.isnan(ref).sum() == 2
+        assert_parity(z, ref, np.abs(ref), rel=rel, what=f"coincident p={p}")
+    # sweep: p > 0 planes poisoned, p = 0 plane is the plain mean there (Pow(d, -0) = 1), p < 0: h = 0
+    zs = V.solve(ps, xi, yi, [1.7, 0.0, -1.0], ctx=ctx)
+    for e, p in enumerate((1.7, 0.0, -1.0)):
+        ref = O.full_solve(o_ps(ps), o_info(xi), o_info(yi), p)
+        assert_parity(zs[e], ref, np.abs(ref), what=f"mixed sweep p={p}")
+    x[77] = np.nan
+    ps = _stale(x, y, w)
+    keyed = V.PointSet(ps.x, ps.y, ps.w, ps.key_r.copy(), ps.key_c.copy())
+    keyed.key_r[5], keyed.key_c[5] = 7, 9                              # one real exact hit survives the NaN flood
+    for p, precision in ((1.7, _lib.FP64), (2.0, _lib.FP64), (2.0, _lib.FP32), (1.5, _lib.FP64)):
+        z = V.solve(keyed, xi, yi, [p], precision=precision, ctx=ctx)[0]
+        ref = O.full_solve(o_ps(keyed), o_info(xi), o_info(yi), p)
+        assert np.isnan(ref).sum() == ref.size - 1 and ref[7, 9] == w[5]
+        assert np.array_equal(np.isnan(z), np.isnan(ref)) and z[7, 9] == w[5], (p, precision)
+
+
+def test_sweep_longer_than_64_exponents(ctx):
+    """cmd/idw.go accepts any --es/--ee/--ei: a sweep of 70 exponents runs as 7 passes of 10 in one call"""
+    ps, xi, yi = random_case(61, 300, 24, 40, step=2.0)
+    exps = V.exp_range(0.1, 7.05, 0.1)
+    assert len(exps) == 70
+    zs = V.solve(ps, xi, yi, exps, ctx=ctx)
+    for e in (0, 9, 10, 33, 69):
+        ref, scale = oracle_ref(ps, xi, yi, float(exps[e]))
+        assert_parity(zs[e], ref, scale, what=f"70-sweep e={e}")

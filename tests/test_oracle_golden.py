@@ -162,3 +162,22 @@ def test_edge_semantics():
     assert zn[1, 1] == 9.0
     empty = O.PointSet(*(np.empty(0) for _ in range(3)), np.empty(0, np.int64), np.empty(0, np.int64))
     assert np.isnan(O.full_solve(empty, xinfo, yinfo, 2.0, 4, 4)).all()   # N = 0 -> 0/0
+
+
+def test_summation_order_modes_of_the_cell_solver():
+    """solve_cells(mode=...): input order, reverse order (another valid execution of the reference: its Go map is
+    iterated in a random order) and the same float64 terms summed in long double agree to rounding on a small case,
+    exact hits are returned verbatim in every mode, and the default mode is the input-order one."""
+    rng = np.random.default_rng(3)
+    xi, yi = O.Info(0, 99, 1.0), O.Info(0, 79, 1.0)
+    ps = O.make_coord_space(rng.uniform(0, 100, 3000), rng.uniform(0, 80, 3000), rng.normal(0, 50, 3000), xi, yi)
+    rr, cc = rng.integers(0, 80, 200), rng.integers(0, 100, 200)
+    rr[:5], cc[:5] = ps.key_r[:5], ps.key_c[:5]
+    for p in (0.5, 1.7, 2.0, 4.5):
+        a = O.solve_cells(ps, xi, yi, p, rr, cc)
+        b = O.solve_cells(ps, xi, yi, p, rr, cc, mode=O.ORDER_REVERSE)
+        c = O.solve_cells(ps, xi, yi, p, rr, cc, mode=O.SUM_LONG_DOUBLE)
+        assert np.array_equal(a, O.solve_cells(ps, xi, yi, p, rr, cc, nthreads=1, mode=O.ORDER_INPUT))
+        assert np.array_equal(a[:5], ps.w[:5]) and np.array_equal(b[:5], ps.w[:5]) and np.array_equal(c[:5], ps.w[:5])
+        scale = np.maximum(np.abs(c), O.solve_cells(O.PointSet(ps.x, ps.y, np.abs(ps.w), ps.key_r, ps.key_c), xi, yi, p, rr, cc))
+        assert np.max(np.abs(a - c) / scale) < 2e-13 and np.max(np.abs(b - c) / scale) < 2e-13

@@ -6,8 +6,8 @@ the reference's names: FullSolve, ChunkSolve, MakeCoordSpace, GetDimensions, ...
 There is no CPU fallback: importing works anywhere, computing needs the library and a GPU.
 """
 from . import _lib  # noqa: F401
-from .idw import (ChunkSolve, FullSolve, GetDimensions, IdwContext, Info, MakeCoordSpace, PointSet,  # noqa: F401
-                  PointToPair, exp_range, solve)
+from .idw import (ChunkSolve, FullSolve, GetDimensions, IdwContext, Info, MakeCoordSpace, PinnedArray,  # noqa: F401
+                  PointSet, PointToPair, exp_range, solve)
 
 __all__ = ["FullSolve", "ChunkSolve", "MakeCoordSpace", "GetDimensions", "PointToPair", "Info", "PointSet",
-           "IdwContext", "exp_range", "solve"]
+           "IdwContext", "PinnedArray", "exp_range", "solve"]

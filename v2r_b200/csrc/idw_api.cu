@@ -523,7 +523,9 @@ static int end_session(v2r_idw_ctx *ctx) {
         float ms = 0;
         // span first kernel -> last kernel on this device (includes waits for a free band buffer, if any)
         if (d.k_any && cudaEventElapsedTime(&ms, d.k_first, d.k_last) == cudaSuccess) ctx->kernel_ms = std::max(ctx->kernel_ms, (double)ms);
-        if (d.c_any && cudaEventElapsedTime(&ms, d.c_first, d.c_last) == cudaSuccess) ctx->d2h_ms = std::max(ctx->d2h_ms, (double)ms);
+        // copy-out that was NOT hidden behind kernels: end of this device's last kernel -> end of its last copy
+        // (copies of earlier rounds overlap the kernels of later ones)
+        if (d.k_any && d.c_any && cudaEventElapsedTime(&ms, d.k_last, d.c_last) == cudaSuccess) ctx->d2h_ms = std::max(ctx->d2h_ms, (double)std::max(ms, 0.0f));
     }
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->dev[0].up_start, ctx->dev[0].up_stop) == cudaSuccess) ctx->h2d_ms = ms;

@@ -231,10 +231,11 @@ __device__ __forceinline__ unsigned run_piece(const KParams &p, Body &body, unsi
             __threadfence();
             const double *src = p.scratch + (slot * K * NACC) * THREADS + tid;
 #pragma unroll
-            for (int i = 0; i < NACC; ++i) {
-                double tot = __ldcg(src + (long long)i * THREADS);
-                for (int s = 1; s < K; ++s) tot += __ldcg(src + ((long long)s * NACC + i) * THREADS);
-                body.acc[i] = tot;
+            for (int i = 0; i < NACC; ++i) body.acc[i] = __ldcg(src + (long long)i * THREADS);
+            for (int s = 1; s < K; ++s) {  // segment order, NACC independent loads in flight per step
+                src += (long long)NACC * THREADS;
+#pragma unroll
+                for (int i = 0; i < NACC; ++i) body.acc[i] += __ldcg(src + (long long)i * THREADS);
             }
             body.store(p);
             if (tid == 0) p.counters[slot] = 0;  // leave the counters clean for the next launch
@@ -349,28 +350,47 @@ __device__ __forceinline__ void weights(double d2, const KParams &p, const GenTa
 // Tile guard of the paired kernels.  Pairing two points under one reciprocal needs the product of their squared
 // distances to stay a normal double for EVERY cell of the CTA tile.  A point is unsafe for the tile when some cell
 // is closer than `tiny` to it in both axes (or it coincides with a node: d2 == 0 must yield NaN through the
-// one-reciprocal code) or farther than `far` in either axis; NaN coordinates are unsafe too.  O(1) per point:
-// the nearest node column / row of the tile is found by rounding, its neighbours cover the rounding of the division.
-template <typename F>
-__device__ __forceinline__ bool pairing_unsafe(double x, double y, const KParams &p, long long c_lo, long long c_hi,
-                                               long long r_lo, long long r_hi, F tiny, F far) {
-    auto axis = [&](double v, double vmin, double step, double inv_step, long long lo, long long hi, double &dmin, double &dmax) {
-        const double q = rint((v - vmin) * inv_step);
-        long long k = (q >= (double)hi) ? hi : ((q <= (double)lo) ? lo : (long long)q);  // NaN -> lo
-        dmin = INFINITY;
+// one-reciprocal code) or farther than `far` in either axis; NaN coordinates are unsafe too.
+// Cost matters (two points per thread and point tile): a dozen FP64 compares decide every point that is not within
+// one cell of the tile's bounding box; only those few go through the exact nearest-node distances.
+struct TileBox {
+    double xlo, xhi, ylo, yhi;  // coordinates of the tile's extreme nodes
+    double wx, wy;              // extent + two cells: a point with |x-xlo| + |x-xhi| <= wx lies within one cell of the tile
+    double c0, r0;              // first column / row of the tile as doubles
+};
+template <int W, int H>
+__device__ __forceinline__ TileBox tile_box(const KParams &p, long long tc0, long long tr0) {
+    TileBox b;
+    b.c0 = (double)tc0;
+    b.r0 = (double)tr0;
+    b.xlo = __dadd_rn(p.x_min, __dmul_rn(b.c0, p.x_step));
+    b.xhi = __dadd_rn(p.x_min, __dmul_rn(b.c0 + (W - 1), p.x_step));
+    b.ylo = __dadd_rn(p.y_min, __dmul_rn(b.r0, p.y_step));
+    b.yhi = __dadd_rn(p.y_min, __dmul_rn(b.r0 + (H - 1), p.y_step));
+    b.wx = fabs(b.xhi - b.xlo) + 2.0 * fabs(p.x_step);
+    b.wy = fabs(b.yhi - b.ylo) + 2.0 * fabs(p.y_step);
+    return b;
+}
+template <int W, int H>
+__device__ __forceinline__ bool pairing_unsafe(double x, double y, const KParams &p, const TileBox &b, double tiny, double far) {
+    const double ax0 = fabs(x - b.xlo), ax1 = fabs(x - b.xhi), ay0 = fabs(y - b.ylo), ay1 = fabs(y - b.yhi);
+    if (!(ax0 <= far && ax1 <= far && ay0 <= far && ay1 <= far)) return true;  // too far, or NaN
+    if (!(ax0 + ax1 <= b.wx && ay0 + ay1 <= b.wy)) return false;               // more than a cell away from every node
+    // near the tile (rare): exact distance to the nearest node column / row; +-1 covers the rounding of the division
+    auto nearest = [](double v, double lo, double vmin, double step, double inv_step, double first, int count) {
+        int k = __double2int_rn((v - lo) * inv_step);
+        k = min(max(k, 0), count - 1);
+        double dmin = INFINITY;
 #pragma unroll
         for (int d = -1; d <= 1; ++d) {
-            long long kk = k + d;
-            kk = kk < lo ? lo : (kk > hi ? hi : kk);
-            dmin = fmin(dmin, fabs(v - __dadd_rn(vmin, __dmul_rn((double)kk, step))));
+            const int kk = min(max(k + d, 0), count - 1);
+            dmin = fmin(dmin, fabs(v - __dadd_rn(vmin, __dmul_rn(first + (double)kk, step))));
         }
-        dmax = fmax(fabs(v - __dadd_rn(vmin, __dmul_rn((double)lo, step))), fabs(v - __dadd_rn(vmin, __dmul_rn((double)hi, step))));
+        return dmin;
     };
-    double xmin_d, xmax_d, ymin_d, ymax_d;
-    axis(x, p.x_min, p.x_step, p.inv_x_step, c_lo, c_hi, xmin_d, xmax_d);
-    axis(y, p.y_min, p.y_step, p.inv_y_step, r_lo, r_hi, ymin_d, ymax_d);
-    const bool safe = (xmin_d >= (double)tiny || ymin_d >= (double)tiny) && xmax_d <= (double)far && ymax_d <= (double)far;
-    return !safe;  // NaN anywhere -> comparisons false -> unsafe
+    const double dx = nearest(x, b.xlo, p.x_min, p.x_step, p.inv_x_step, b.c0, W);
+    const double dy = nearest(y, b.ylo, p.y_min, p.y_step, p.inv_y_step, b.r0, H);
+    return !(dx >= tiny || dy >= tiny);
 }
 
 // ---------------------------------------------------------------------------- FP64 body
@@ -384,15 +404,19 @@ struct Fp64Body {
     static constexpr int THREADS = THREADS_;
     static constexpr int WARPS = THREADS / 32;
     static constexpr int NACC = 2 * E * CR * CC;  // acc[((e*CR + a)*CC + b)*2 + {0: num, 1: den}]
-    static constexpr int BODY_BYTES = (MODE == MODE_GEN) ? (int)sizeof(GenTables) : 0;
-    static constexpr int UNR = PAIRED > 1 ? PAIRED : 1;
+    // PAIRED == 2: the squared row distances of a half point tile are computed ONCE per CTA into shared memory
+    // ([point][row of the tile], 256 x 32 doubles) instead of by each of the 32 lanes of every warp
+    static constexpr int YS_POINTS = kTilePoints / 2;
+    static constexpr int BODY_BYTES = (MODE == MODE_GEN) ? (int)sizeof(GenTables) : (PAIRED == 2 ? YS_POINTS * WARPS * CR * (int)sizeof(double) : 0);
 
     double acc[NACC];
     double cx[CC], cy[CR];
     int tile_r, tile_c;         // tile indices of the CTA tile
     const GenTables *gt;
+    double *ys;                 // PAIRED == 2: staged squared row distances
 
-    __device__ __forceinline__ Fp64Body(const KParams &p, unsigned char *smem) : gt(nullptr) {
+    __device__ __forceinline__ Fp64Body(const KParams &p, unsigned char *smem) : gt(nullptr), ys(nullptr) {
+        if constexpr (PAIRED == 2) ys = reinterpret_cast<double *>(smem + kStageBytes + kCtrlBytes);
         if constexpr (MODE == MODE_GEN) {
             // copy the table image global -> shared; single-exponent safe passes fold 512 c into log2_c
             GenTables *t = reinterpret_cast<GenTables *>(smem + kStageBytes + kCtrlBytes);
@@ -455,15 +479,64 @@ struct Fp64Body {
             static_assert(MODE == MODE_RCP && E == 1 && K0 == 1, "pairing is the p = 2 trick");
             const int slot = it & 1;
             bool unsafe = false;
-            const long long tc0 = (long long)tile_c * (32 * CC), tr0 = p.row0 + (long long)tile_r * (WARPS * CR);
+            const TileBox box = tile_box<32 * CC, WARPS * CR>(p, (long long)tile_c * (32 * CC), p.row0 + (long long)tile_r * (WARPS * CR));
             for (int k = threadIdx.x; k < cnt; k += THREADS)
-                unsafe |= pairing_unsafe(sx[k], sy[k], p, tc0, tc0 + 32 * CC - 1, tr0, tr0 + WARPS * CR - 1, 0x1p-250, 0x1p+249);
+                unsafe |= pairing_unsafe<32 * CC, WARPS * CR>(sx[k], sy[k], p, box, 0x1p-250, 0x1p+249);
             if (unsafe) ctrl->guard[slot] = 1;
             __syncthreads();
             const bool paired_ok = !ctrl->guard[slot];
             if (threadIdx.x == 0) ctrl->guard[slot ^ 1] = 0;  // nobody touches the other slot until the next tile
-            if (paired_ok) {
-#pragma unroll UNR
+            if constexpr (PAIRED == 2) {
+                constexpr int H = WARPS * CR;  // rows of the CTA tile
+                static_assert(H == 32, "one lane per tile row in the staging pass");
+                if (paired_ok) {
+                    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                    // this lane's row in the staging pass (RCToPoint, tools/utils.go:78-82)
+                    const double cyr = __dadd_rn(p.y_min, __dmul_rn((double)(p.row0 + (long long)tile_r * H + lane), p.y_step));
+                    const int even = cnt & ~1;
+                    for (int h0 = 0; h0 < even; h0 += YS_POINTS) {
+                        const int hn = min(YS_POINTS, even - h0);
+                        if (h0) __syncthreads();  // the previous half has been consumed
+                        for (int k = warp; k < hn; k += WARPS) {
+                            const double d = __dsub_rn(sy[h0 + k], cyr);
+                            ys[k * H + lane] = __dmul_rn(d, d);
+                        }
+                        __syncthreads();
+                        const double2 *yq = reinterpret_cast<const double2 *>(ys + warp * CR);
+#pragma unroll 1
+                        for (i = h0; i < h0 + hn; i += 2, yq += H) {
+                            const double2 x = *reinterpret_cast<const double2 *>(sx + i);
+                            const double2 w = *reinterpret_cast<const double2 *>(sw + i);
+                            double ax[CC], bx[CC], ay[CR], by[CR];
+#pragma unroll
+                            for (int b = 0; b < CC; ++b) {
+                                double d0 = __dsub_rn(x.x, cx[b]), d1 = __dsub_rn(x.y, cx[b]);
+                                ax[b] = __dmul_rn(d0, d0);
+                                bx[b] = __dmul_rn(d1, d1);
+                            }
+#pragma unroll
+                            for (int a = 0; a < CR; a += 2) {
+                                const double2 u = yq[a / 2], v = yq[H / 2 + a / 2];
+                                ay[a] = u.x; ay[a + 1] = u.y;
+                                by[a] = v.x; by[a + 1] = v.y;
+                            }
+#pragma unroll
+                            for (int a = 0; a < CR; ++a)
+#pragma unroll
+                                for (int b = 0; b < CC; ++b) {
+                                    const double A = __dadd_rn(ax[b], ay[a]), B = __dadd_rn(bx[b], by[a]);
+                                    const double r = pow_m1(A * B);
+                                    const double N = fma(w.x, B, w.y * A);
+                                    double &num = acc[(a * CC + b) * 2], &den = acc[(a * CC + b) * 2 + 1];
+                                    num = fma(N, r, num);
+                                    den = fma(A + B, r, den);
+                                }
+                        }
+                    }
+                    i = even;
+                }
+            } else if (paired_ok) {
+#pragma unroll 1
                 for (; i + 1 < cnt; i += 2) {
                     const double2 x = *reinterpret_cast<const double2 *>(sx + i);
                     const double2 y = *reinterpret_cast<const double2 *>(sy + i);

@@ -333,7 +333,11 @@ struct Fp32PackedBody {
                 const float2 dx = col_d(xh, xl, j);
 #pragma unroll
                 for (int a = 0; a < CR; ++a) {
-                    const float2 A = __ffma2_rn(dx, dx, ay[a]);
+                    float2 A = __ffma2_rn(dx, dx, ay[a]);
+                    // cell units lose offsets below ~1e-14 cells: a point that close (but not ON the node -- those cells
+                    // are poisoned afterwards) must still dominate its cell with a finite weight; NaN passes through
+                    A.x = A.x < 0x1p-60f ? 0x1p-60f : A.x;
+                    A.y = A.y < 0x1p-60f ? 0x1p-60f : A.y;
                     const float2 r = make_float2(frcp(A.x), frcp(A.y));
                     pn[a][j] = __ffma2_rn(w, r, pn[a][j]);
                     pd[a][j] = __fadd2_rn(pd[a][j], r);

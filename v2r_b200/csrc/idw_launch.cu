@@ -106,6 +106,9 @@ struct Variant {
 };
 
 #define V2R_SMEM(MODE, E, CR, CC, THREADS) smem_bytes((MODE) == MODE_GEN ? (int)sizeof(GenTables) : 0, 2 * (E) * (CR) * (CC), THREADS)
+#define V2R_PAIRED_YS(TAG, CR, CC, THREADS, MINB)                                                                                     \
+    Variant { MODE_RCP, 1, 1, 0, CR, CC, THREADS, idw_fp64_kernel<MODE_RCP, 1, CR, CC, 1, 0, THREADS, MINB, 2>, "MODE_RCP", true, TAG, \
+              smem_bytes(Fp64Body<MODE_RCP, 1, CR, CC, 1, 0, THREADS, 2>::BODY_BYTES, 2 * (CR) * (CC), THREADS) }
 #define V2R_VARIANT(MODE, E, CR, CC, K0, DK, THREADS, MINB)                                                                     \
     Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE, false, nullptr, \
               V2R_SMEM(MODE, E, CR, CC, THREADS) }
@@ -135,9 +138,10 @@ static const Variant kVariants[] = {
     // tuning builds (V2R_IDW_TUNE=<tag>), kept to document what was measured; never picked by default
     V2R_TUNE("g2x2", MODE_GEN, 1, 2, 2, GEN_SINGLE, 0, 256, 2), V2R_TUNE("g4x4", MODE_GEN, 1, 4, 4, GEN_SINGLE, 0, 256, 1),
     V2R_TUNE("g4x2", MODE_GEN, 1, 4, 2, GEN_SINGLE, 0, 256, 2),
-    V2R_PAIRED("c4x6", 4, 6, 256, 1),
+    V2R_PAIRED("c4x6", 4, 6, 256, 1), V2R_PAIRED_YS("ys4x6", 4, 6, 256, 1),
+    V2R_PAIRED("nys", 4, 4, 256, 1),                // p = 2, paired, every lane computes its own dy^2 (round 1's loop)
     // compile-time ladders for the headline shapes (looked up first)
-    V2R_PAIRED(nullptr, 4, 4, 256, 1),              // p = 2, paired (c2, c4)
+    V2R_PAIRED_YS(nullptr, 4, 4, 256, 1),           // p = 2, paired, dy^2 staged in shared memory once per CTA (c2, c4)
     V2R_VARIANT(MODE_RCP, 1, 4, 4, 1, 0, 256, 1),   // p = 2, one reciprocal per pair (V2R_IDW_FP64_PAIRED=0)
     // rsqrt / root4 bases have longer dependent chains: 2x4 cells at two CTAs per SM measured +8 % over 4x4 at one
     V2R_VARIANT(MODE_RSQ, 1, 2, 4, 1, 0, 256, 2),   // p = 1
@@ -202,6 +206,8 @@ static double model_ops(const Pass &ps, const Variant &v) {
     } else {
         ops += ps.mode == MODE_RCP ? 3 : (ps.mode == MODE_RSQ ? 5 : 7);
         if (v.paired) ops -= 0.5;  // 11 instead of 12 instructions per two pairs
+        if (v.paired && v.fn == (void (*)(const KParams))idw_fp64_kernel<MODE_RCP, 1, 4, 4, 1, 0, 256, 1, 2>)
+            ops -= 2.0 / v.cc;     // dy, dy^2 come from shared memory (computed once per CTA, not per lane)
         ops += ladder(ps.k0);
         if (E > 1) ops += ladder(ps.dk) + (E - 1);
     }

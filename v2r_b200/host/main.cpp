@@ -153,17 +153,19 @@ int run_idw(int argc, char **argv) {
         opt.n_gpus = (int)F.gpus;
         opt.fp32 = F.fp32;
         opt.progress = [](const std::string &m) { info(m); };
-        int64_t band = 0;
-        if (F.useChunking) {  // ChunkSolve semantics: --cy is the streamed band height (idw_chunk.go:48-53 for oversize chunks)
+        int64_t band = 0, chunkC = 0;
+        if (F.useChunking) {  // ChunkSolve semantics: --cy x --cx is the write window (idw_chunk.go:48-53 for oversize chunks)
             band = F.idwChunkY;
+            chunkC = F.idwChunkX;
             if (F.idwChunkY > rows || F.idwChunkX > cols) {
                 logf(1, "WARN", "chunk size too large for total image; Chunk sizes changed to ~1/16 of total size");
                 band = rows / 4;
+                chunkC = cols / 4;
             }
-            if (band <= 0) fatal("chunk size is not usable for this grid");
+            if (band <= 0 || chunkC <= 0) fatal("chunk size is not usable for this grid");
         }
         int iterations = 0;
-        idw::SweepSolve(data, outs, rd.xInfo, rd.yInfo, rd.proj, pows, band, [&](const std::string &m) { ++iterations; debug(m); }, opt);
+        idw::SweepSolve(data, outs, rd.xInfo, rd.yInfo, rd.proj, pows, band, [&](const std::string &m) { ++iterations; debug(m); }, opt, chunkC);
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
         info("Completed " + std::to_string(iterations) + " iterations in " + fmt("%g", secs) + "s");
         info("Outfiles: " + outfile + "pow{EXP}.{EXT}");

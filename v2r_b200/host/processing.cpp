@@ -234,8 +234,10 @@ ReadResult ReadGeoPackage(const std::string &filename, const std::string &layer,
     r.points = tools::PointSet(1024);
     r.xInfo.Step = stepX;
     r.yInfo.Step = stepY;
-    Stmt s(db, "select " + quote_ident(geom_col) + ", " + quote_ident(field) + " from " + quote_ident(layer) + " order by fid");
-    while (s.row()) {  // features in fid order like l.Feature(1..count) (io_gdal.go:180-190)
+    Stmt s(db, "select " + quote_ident(geom_col) + ", " + quote_ident(field) + " from " + quote_ident(layer) + " order by rowid");
+    // features in FID order like l.Feature(1..count) (io_gdal.go:180-190).  A GeoPackage feature table's primary key is
+    // an INTEGER PRIMARY KEY, i.e. an alias of SQLite's rowid whatever its name is (fid, OBJECTID, id ...)
+    while (s.row()) {
         const unsigned char *b = (const unsigned char *)sqlite().column_blob(s.st, 0);
         int nb = sqlite().column_bytes(s.st, 0);
         if (!b || nb < 8 || b[0] != 'G' || b[1] != 'P') throw Error("not a GeoPackageBinary geometry");

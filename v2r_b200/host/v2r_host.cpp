@@ -132,9 +132,14 @@ static std::string fmt_g(double v) {
     return b;
 }
 
+// one streaming session: at most kMaxSweep exponents (include/v2r_idw.h)
+static void SweepSession(v2r_idw_ctx *ctx, const tools::PointSet &data, const std::string *outfiles, const tools::Info &xInfo,
+                         const tools::Info &yInfo, int64_t rows, int64_t cols, const std::string &proj, const double *pows, int E,
+                         int64_t bandRows, int64_t chunkC, const Options &opt);
+
 void SweepSolve(const tools::PointSet &data, const std::vector<std::string> &outfiles, const tools::Info &xInfo,
                 const tools::Info &yInfo, const std::string &proj, const std::vector<double> &pows, int64_t bandRows,
-                const Channel &channel, const Options &opt) {
+                const Channel &channel, const Options &opt, int64_t chunkC) {
     const auto start = std::chrono::steady_clock::now();
     if (outfiles.size() != pows.size() || pows.empty()) throw Error("one outfile per exponent is required");
     for (const auto &f : outfiles) check_outfile(f);
@@ -143,10 +148,23 @@ void SweepSolve(const tools::PointSet &data, const std::vector<std::string> &out
     tools::GetDimensions(xInfo, yInfo, rows, cols);
     if (rows < 0 || cols < 0) throw Error("negative grid dimensions");
     v2r_idw_ctx *ctx = Context(opt);
+    constexpr size_t kMaxSweep = 4096;  // exponents per library call; a longer sweep runs as several sessions
+    for (size_t e0 = 0; e0 < pows.size(); e0 += kMaxSweep) {
+        const size_t e1 = std::min(pows.size(), e0 + kMaxSweep);
+        SweepSession(ctx, data, outfiles.data() + e0, xInfo, yInfo, rows, cols, proj, pows.data() + e0, (int)(e1 - e0), bandRows, chunkC, opt);
+    }
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    if (channel)
+        for (double p : pows)
+            channel("pow" + fmt_g(p) + " [" + std::to_string(rows) + "X" + std::to_string(cols) + "] completed in " + fmt_g(secs) + "s");
+}
+
+static void SweepSession(v2r_idw_ctx *ctx, const tools::PointSet &data, const std::string *outfiles, const tools::Info &xInfo,
+                         const tools::Info &yInfo, int64_t rows, int64_t cols, const std::string &proj, const double *pows, int E,
+                         int64_t bandRows, int64_t chunkC, const Options &opt) {
     v2r_idw_grid grid{xInfo.Min, xInfo.Step, yInfo.Min, yInfo.Step, rows, cols};
-    const int E = (int)pows.size();
     bool asc = false;
-    for (const auto &f : outfiles) asc |= ends_with(f, ".asc");
+    for (int e = 0; e < E; ++e) asc |= ends_with(outfiles[e], ".asc");
     int64_t band = bandRows > 0 ? bandRows : rows;
     if (!asc && bandRows <= 0) {  // ~1 GiB of raster per band unless the caller fixed the height
         int64_t cap = (int64_t(1) << 27) / (std::max<int64_t>(cols, 1) * E);
@@ -160,11 +178,12 @@ void SweepSolve(const tools::PointSet &data, const std::vector<std::string> &out
     struct Free { void *p; ~Free() { v2r_idw_free_pinned(p); } } guard{outp};
     double *out = (double *)outp;
 
-    check(v2r_idw_stream_begin(ctx, data.x, data.y, data.w, data.key_r, data.key_c, data.size(), &grid, pows.data(), E,
+    check(v2r_idw_stream_begin(ctx, data.x, data.y, data.w, data.key_r, data.key_c, data.size(), &grid, pows, E,
                                opt.fp32 ? V2R_IDW_FP32 : V2R_IDW_FP64, band), "v2r_idw_stream_begin");
     struct End { v2r_idw_ctx *c; ~End() { v2r_idw_stream_end(c); } } end_guard{ctx};
     processing::GDalInfo gd = processing::CreateGDalInfo(xInfo.Min, yInfo.Min, xInfo.Step, yInfo.Step, 7, proj);
     std::vector<char> created(E, 0);
+    std::vector<double> window;
     if (rows == 0 || cols == 0)
         for (int e = 0; e < E; ++e) processing::WriteGDAL(out, gd, outfiles[e], {0, 0}, {rows, cols}, {0, 0}, true);
     // progress like ChunkSolve's "~10%, i / total" lines (features/idw/idw_chunk.go:77,92-96), per streamed band
@@ -179,15 +198,24 @@ void SweepSolve(const tools::PointSet &data, const std::vector<std::string> &out
             opt.progress("~" + std::to_string(std::min<int64_t>(100, 100 * done / total_bands)) + "%, " + std::to_string(done) + " / " +
                          std::to_string(total_bands));
         const int64_t plane = nr * cols;
+        // windows of chunkC columns at (r0, c0), like the reference's per-chunk WriteGDAL (features/idw/idw_chunk.go:69-90,
+        // tools/processing/io_gdal.go:72-73); a full-width band is written as one window
+        const int64_t wcols = (chunkC > 0 && chunkC < cols) ? chunkC : cols;
         for (int e = 0; e < E; ++e) {  // the next band is already computing while these windows are written
-            processing::WriteGDAL(out + (int64_t)e * plane, gd, outfiles[e], {r0, 0}, {rows, cols}, {nr, cols}, !created[e]);
-            created[e] = 1;
+            const double *flat = out + (int64_t)e * plane;
+            for (int64_t c0 = 0; c0 < cols; c0 += wcols) {
+                const int64_t wc = std::min(wcols, cols - c0);
+                const double *buf = flat;
+                if (wc != cols) {  // WriteGDAL takes a contiguous window
+                    window.resize((size_t)(nr * wc));
+                    for (int64_t r = 0; r < nr; ++r) memcpy(&window[(size_t)(r * wc)], flat + r * cols + c0, (size_t)wc * sizeof(double));
+                    buf = window.data();
+                }
+                processing::WriteGDAL(buf, gd, outfiles[e], {r0, c0}, {rows, cols}, {nr, wc}, !created[e]);
+                created[e] = 1;
+            }
         }
     }
-    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
-    if (channel)
-        for (double p : pows)
-            channel("pow" + fmt_g(p) + " [" + std::to_string(rows) + "X" + std::to_string(cols) + "] completed in " + fmt_g(secs) + "s");
 }
 
 void FullSolve(const tools::PointSet &data, const std::string &outfile, const tools::Info &xInfo, const tools::Info &yInfo,
@@ -202,9 +230,9 @@ void ChunkSolve(const tools::PointSet &data, const std::string &outfile, const t
     tools::GetDimensions(xInfo, yInfo, rows, cols);
     if (chunkR > rows || chunkC > cols) { chunkR = rows / 4; chunkC = cols / 4; }  // features/idw/idw_chunk.go:48-53
     if (chunkR <= 0 || chunkC <= 0) throw Error("chunk size is not usable for this grid");
-    // On the GPU a chunk is a write granule: bands of chunkR rows stream out while the next band computes.
-    // chunkC has no GPU meaning (bands are full-width windows, which WriteGDAL accepts).
-    SweepSolve(data, {outfile}, xInfo, yInfo, proj, {pow}, chunkR, channel, opt);
+    // On the GPU a chunk is a write granule: bands of chunkR rows stream out while the next band computes and are
+    // written as windows of chunkC columns, the reference's chunk-write protocol.
+    SweepSolve(data, {outfile}, xInfo, yInfo, proj, {pow}, chunkR, channel, opt, chunkC);
 }
 
 }  // namespace idw

@@ -101,7 +101,7 @@ v2r_idw_ctx *Context(const Options &opt);
 
 void SweepSolve(const tools::PointSet &data, const std::vector<std::string> &outfiles, const tools::Info &xInfo,
                 const tools::Info &yInfo, const std::string &proj, const std::vector<double> &pows, int64_t bandRows,
-                const Channel &channel, const Options &opt = {});
+                const Channel &channel, const Options &opt = {}, int64_t chunkC = 0);
 void FullSolve(const tools::PointSet &data, const std::string &outfile, const tools::Info &xInfo, const tools::Info &yInfo,
                const std::string &proj, double pow, const Channel &channel, const Options &opt = {});
 void ChunkSolve(const tools::PointSet &data, const std::string &outfile, const tools::Info &xInfo, const tools::Info &yInfo,

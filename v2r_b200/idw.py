@@ -101,6 +101,30 @@ def make_grid(xInfo: Info, yInfo: Info, rows=None, cols=None) -> Grid:
     return Grid(xInfo.min, xInfo.step, yInfo.min, yInfo.step, rows, cols)
 
 
+class PinnedArray:
+    """A numpy view of page-locked host memory from v2r_idw_alloc_pinned (what the readers of the C++ / Go hosts fill):
+    copies to and from it are asynchronous DMA, and a multi-GPU context copies every device's band straight into it."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self._L = _lib.load()
+        self._p = C.c_void_p()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        check(self._L.v2r_idw_alloc_pinned(max(n, 8), C.byref(self._p)))
+        self.array = np.ctypeslib.as_array((C.c_byte * max(n, 8)).from_address(self._p.value))[:n].view(dtype).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            self._L.v2r_idw_free_pinned(self._p)
+            self._p = C.c_void_p()
+
+    def __enter__(self):
+        return self.array
+
+    def __exit__(self, *a):
+        self.free()
+
+
 class IdwContext:
     """v2r_idw_ctx: one process driving n_gpus devices, or one given device."""
 
@@ -143,23 +167,33 @@ class IdwContext:
     def solve(self, ps: PointSet, grid: Grid, exps, precision: int = FP64, out=None):
         return self.solve_rows(ps, grid, 0, grid.rows, exps, precision, out)
 
-    def stream(self, ps: PointSet, grid: Grid, exps, precision: int = FP64, band_rows: int = 0):
-        """Generator over (row0, band[E, nrows, cols]) -- the chunk-write protocol of ChunkSolve."""
+    def stream(self, ps: PointSet, grid: Grid, exps, precision: int = FP64, band_rows: int = 0, pinned: bool = False):
+        """Generator over (row0, band[E, nrows, cols]) -- the chunk-write protocol of ChunkSolve.  pinned=True receives
+        the bands in ONE page-locked buffer (like the C++ / Go hosts): the yielded view is valid until the next step."""
         x, y, w, kr, kc = _f64(ps.x), _f64(ps.y), _f64(ps.w), _i64(ps.key_r), _i64(ps.key_c)
         exps = _f64(np.atleast_1d(exps))
         check(self._L.v2r_idw_stream_begin(self._h, _ptr(x), _ptr(y), _ptr(w), _ptr(kr), _ptr(kc), len(x),
                                            C.byref(grid), _ptr(exps), len(exps), precision, band_rows))
+        pin = None
         try:
             cap = max(band_rows if band_rows > 0 else grid.rows, 1)
+            if pinned:
+                pin = PinnedArray(len(exps) * cap * max(grid.cols, 1))
             while True:
-                buf = np.empty(len(exps) * cap * max(grid.cols, 1))
+                buf = pin.array if pin is not None else np.empty(len(exps) * cap * max(grid.cols, 1))
                 r0, nr = C.c_int64(), C.c_int64()
                 check(self._L.v2r_idw_stream_next(self._h, _ptr(buf), C.byref(r0), C.byref(nr)))
                 if nr.value == 0:
                     break
                 yield r0.value, buf[:len(exps) * nr.value * grid.cols].reshape(len(exps), nr.value, grid.cols)
         finally:
-            check(self._L.v2r_idw_stream_end(self._h))
+            rc = self._L.v2r_idw_stream_end(self._h)
+            if pin is not None:
+                pin.free()
+            check(rc)
+
+    def last_error(self) -> str:
+        return self._L.v2r_idw_ctx_last_error(self._h).decode(errors="replace")
 
     def last_timing(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()

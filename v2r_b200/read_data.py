@@ -59,7 +59,7 @@ def ReadGeoPackage(filename: str, layer: str, field: str, stepX: float, stepY: f
         cols = [r[1] for r in con.execute(f'pragma table_info("{layer}")')]
         if field not in cols:
             raise ValueError(f"field {field} not in layer {layer}")
-        rows = con.execute(f'select "{geom_col}", "{field}" from "{layer}" order by fid').fetchall()
+        rows = con.execute(f'select "{geom_col}", "{field}" from "{layer}" order by rowid').fetchall()
     finally:
         con.close()
     n = len(rows)

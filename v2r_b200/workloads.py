@@ -76,8 +76,9 @@ def write_txt(path: str, x, y, w, xInfo: Info, yInfo: Info):
         f.write(f"STEP\n{float(xInfo.step)!r} {float(yInfo.step)!r}\nESTIMATE\n{float(xInfo.min)!r} {float(xInfo.max)!r}\n{float(yInfo.min)!r} {float(yInfo.max)!r}")
 
 
-def write_gpkg(path: str, x, y, w, layer="wsels", field="elevation", srs_id=2284, wkt="EPSG:2284"):
-    """A GeoPackage with the fixture's schema (features/idw/idw_test_files/input.gpkg)."""
+def write_gpkg(path: str, x, y, w, layer="wsels", field="elevation", srs_id=2284, wkt="EPSG:2284", pk="fid"):
+    """A GeoPackage with the fixture's schema (features/idw/idw_test_files/input.gpkg); `pk` names the integer primary
+    key column (OGR writes "fid", ArcGIS "OBJECTID", `ogr2ogr -lco FID=id` anything)."""
     import os
     import sqlite3
     import struct
@@ -93,7 +94,7 @@ def write_gpkg(path: str, x, y, w, layer="wsels", field="elevation", srs_id=2284
             min_x DOUBLE, min_y DOUBLE, max_x DOUBLE, max_y DOUBLE, srs_id INTEGER);
         CREATE TABLE gpkg_geometry_columns (table_name TEXT NOT NULL, column_name TEXT NOT NULL,
             geometry_type_name TEXT NOT NULL, srs_id INTEGER NOT NULL, z TINYINT NOT NULL, m TINYINT NOT NULL);
-        CREATE TABLE "{layer}" ("fid" INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, "geom" POINT, "uid" MEDIUMINT, "{field}" REAL);
+        CREATE TABLE "{layer}" ("{pk}" INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, "geom" POINT, "uid" MEDIUMINT, "{field}" REAL);
     """)
     con.execute("insert into gpkg_spatial_ref_sys values (?,?,?,?,?,?)", ("srs", srs_id, "EPSG", srs_id, wkt, None))
     con.execute("insert into gpkg_contents (table_name, data_type, identifier, min_x, min_y, max_x, max_y, srs_id) "
