@@ -87,11 +87,17 @@ for f in sorted(glob.glob("${O}_m${n}_*.json")):
 P
     ;;
 tune)   # tuning builds against the defaults (V2R_IDW_TUNE=<tag>, see the variant tables in csrc/idw_launch*.cu)
-    for t in none ys ys4x6 c4x6; do
-        V2R_IDW_TUNE=$t python bench.py --steps 3 --warmup 3 $Q --workload c2 > ${O}_tune_c2_$t.json 2>> ${O}.err
-        V2R_IDW_TUNE=$t python bench.py --steps 3 --warmup 3 $Q --slab 7168:256 > ${O}_tune_c4r256_$t.json 2>> ${O}.err
+    B="python bench.py --steps 3 --warmup 3 $Q"
+    for t in none nys; do   # nys = every lane computes its own dy^2 (no staging in shared memory)
+        V2R_IDW_TUNE=$t $B --workload c2 > ${O}_tune_c2_$t.json 2>> ${O}.err
+        V2R_IDW_TUNE=$t $B --slab 7168:256 > ${O}_tune_c4r256_$t.json 2>> ${O}.err
+        for p in 1.0 1.5 1.7; do V2R_IDW_TUNE=$t $B --workload c2 --exps=$p --band-rows 512 > ${O}_tune_p${p}_$t.json 2>> ${O}.err; done
+        V2R_IDW_TUNE=$t $B --workload c2 --exps 1.1,1.3,1.5,1.7 --band-rows 512 > ${O}_tune_gen4_$t.json 2>> ${O}.err
+        V2R_IDW_TUNE=$t $B --workload c3 --band-rows 512 > ${O}_tune_c3_$t.json 2>> ${O}.err
+        V2R_IDW_TUNE=$t python bench.py --steps 2 --warmup 3 $Q --workload c5 --band-rows 128 > ${O}_tune_c5_$t.json 2>> ${O}.err
     done
-    for t in none f4x4 f4x8 f2x16; do V2R_IDW_TUNE=$t python bench.py --steps 3 --warmup 3 $Q --workload c2 --precision fp32 > ${O}_tune_fp32_$t.json 2>> ${O}.err; done
+    for t in c4x6 ys4x6; do V2R_IDW_TUNE=$t $B --workload c2 > ${O}_tune_c2_$t.json 2>> ${O}.err; done
+    for t in none f4x4 f2x8 f2x16; do V2R_IDW_TUNE=$t $B --workload c2 --precision fp32 > ${O}_tune_fp32_$t.json 2>> ${O}.err; done
     tail -3 ${O}.err; summ ${O}_tune_*.json ;;
 stream)
     python scripts/stream_timing.py > ${O}_stream_timing.log 2>&1; tail -5 ${O}_stream_timing.log

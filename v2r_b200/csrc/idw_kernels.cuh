@@ -399,24 +399,40 @@ __device__ __forceinline__ bool pairing_unsafe(double x, double y, const KParams
 // w0/a + w1/b = (w0 b + w1 a)/(ab): 11 FP64 instructions per two pairs instead of 12, and half the MUFU
 // traffic.  Needs a*b to stay a normal double; point tiles for which that cannot be guaranteed on this CTA's cells
 // (pairing_unsafe) run through the one-reciprocal loop instead.
-template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS_, int PAIRED>
+//
+// YSP > 0 (staged dy^2): the squared row distances depend on (point, tile row) only, yet every one of the 32 lanes of a
+// warp would compute them.  Instead the CTA computes them ONCE per chunk of YSP points into shared memory
+// ([point][row of the tile]; same two instructions, so the values are bit-identical) and the point loops read
+// their CR rows back with one broadcast load: 2/CC fewer FP64 instructions per pair (p = 2, 4x4 cells: 6.5 -> 6.0).
+
+// points per staged chunk: the largest of 256 / 128 / 64 that still fits the shared-memory budget of MINB CTAs per SM
+__host__ __device__ constexpr int ys_points(int mode, int E, int CR, int CC, int threads, int minb) {
+    const int rows = (threads / 32) * CR;
+    const int fixed = kStageBytes + kCtrlBytes + (mode == MODE_GEN ? (int)sizeof(GenTables) : 0) + 2 * E * CR * CC * threads * 8;
+    const int budget = (227 * 1024) / minb - 1024;
+    for (int pts = 256; pts >= 64; pts /= 2)
+        if (fixed + pts * rows * 8 <= budget) return pts;
+    return 0;
+}
+
+template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS_, bool PAIRED, int YSP>
 struct Fp64Body {
     static constexpr int THREADS = THREADS_;
     static constexpr int WARPS = THREADS / 32;
+    static constexpr int H = WARPS * CR;          // rows of the CTA tile
     static constexpr int NACC = 2 * E * CR * CC;  // acc[((e*CR + a)*CC + b)*2 + {0: num, 1: den}]
-    // PAIRED == 2: the squared row distances of a half point tile are computed ONCE per CTA into shared memory
-    // ([point][row of the tile], 256 x 32 doubles) instead of by each of the 32 lanes of every warp
-    static constexpr int YS_POINTS = kTilePoints / 2;
-    static constexpr int BODY_BYTES = (MODE == MODE_GEN) ? (int)sizeof(GenTables) : (PAIRED == 2 ? YS_POINTS * WARPS * CR * (int)sizeof(double) : 0);
+    static constexpr int TAB_BYTES = (MODE == MODE_GEN) ? (int)sizeof(GenTables) : 0;
+    static constexpr int BODY_BYTES = TAB_BYTES + YSP * H * (int)sizeof(double);
+    static_assert(YSP == 0 || (YSP % 2 == 0 && THREADS % H == 0 && CR % 2 == 0), "staging layout");
 
     double acc[NACC];
     double cx[CC], cy[CR];
     int tile_r, tile_c;         // tile indices of the CTA tile
     const GenTables *gt;
-    double *ys;                 // PAIRED == 2: staged squared row distances
+    double *ys;                 // staged squared row distances [point][tile row]
 
     __device__ __forceinline__ Fp64Body(const KParams &p, unsigned char *smem) : gt(nullptr), ys(nullptr) {
-        if constexpr (PAIRED == 2) ys = reinterpret_cast<double *>(smem + kStageBytes + kCtrlBytes);
+        if constexpr (YSP > 0) ys = reinterpret_cast<double *>(smem + kStageBytes + kCtrlBytes + TAB_BYTES);
         if constexpr (MODE == MODE_GEN) {
             // copy the table image global -> shared; single-exponent safe passes fold 512 c into log2_c
             GenTables *t = reinterpret_cast<GenTables *>(smem + kStageBytes + kCtrlBytes);
@@ -431,7 +447,7 @@ struct Fp64Body {
         }
     }
 
-    __device__ __forceinline__ long long row_base(const KParams &p) const { return p.row0 + (long long)tile_r * (WARPS * CR) + (threadIdx.x >> 5) * CR; }
+    __device__ __forceinline__ long long row_base(const KParams &p) const { return p.row0 + (long long)tile_r * H + (threadIdx.x >> 5) * CR; }
     __device__ __forceinline__ long long col_base() const { return (long long)tile_c * (32 * CC) + (threadIdx.x & 31); }
 
     __device__ __forceinline__ void setup(const KParams &p, int tr, int tc) {
@@ -445,16 +461,28 @@ struct Fp64Body {
         for (int a = 0; a < CR; ++a) cy[a] = __dadd_rn(p.y_min, __dmul_rn((double)(r_base + a), p.y_step));
     }
 
-    __device__ __forceinline__ void single_points(const KParams &p, const double *sx, const double *sy, const double *sw, int i, int cnt) {
+    // one cell-point pair per reciprocal power; yq = this warp's staged dy^2 of point i (YSP > 0) or unused
+    __device__ __forceinline__ void single_points(const KParams &p, const double *sx, const double *sy, const double *sw, int i, int end,
+                                                  const double *yq) {
 #pragma unroll 1
-        for (; i < cnt; ++i) {
-            const double x = sx[i], y = sy[i], w = sw[i];
+        for (; i < end; ++i) {
+            const double x = sx[i], w = sw[i];
             double dx2[CC], dy2[CR];
             // euclidDist(p, p0): point minus cell, each square rounded on its own (tools/utils.go:157)
 #pragma unroll
             for (int b = 0; b < CC; ++b) { double d = __dsub_rn(x, cx[b]); dx2[b] = __dmul_rn(d, d); }
+            if constexpr (YSP > 0) {
 #pragma unroll
-            for (int a = 0; a < CR; ++a) { double d = __dsub_rn(y, cy[a]); dy2[a] = __dmul_rn(d, d); }
+                for (int a = 0; a < CR; a += 2) {
+                    const double2 u = *reinterpret_cast<const double2 *>(yq + a);
+                    dy2[a] = u.x; dy2[a + 1] = u.y;
+                }
+                yq += H;
+            } else {
+                const double y = sy[i];
+#pragma unroll
+                for (int a = 0; a < CR; ++a) { double d = __dsub_rn(y, cy[a]); dy2[a] = __dmul_rn(d, d); }
+            }
 #pragma unroll
             for (int a = 0; a < CR; ++a)
 #pragma unroll
@@ -472,103 +500,97 @@ struct Fp64Body {
         }
     }
 
+    // two points per reciprocal (p = 2); [i, end) holds an even number of points
+    __device__ __forceinline__ void paired_points(const double *sx, const double *sy, const double *sw, int i, int end, const double *yq) {
+#pragma unroll 1
+        for (; i < end; i += 2) {
+            const double2 x = *reinterpret_cast<const double2 *>(sx + i);
+            const double2 w = *reinterpret_cast<const double2 *>(sw + i);
+            double ax[CC], bx[CC], ay[CR], by[CR];
+#pragma unroll
+            for (int b = 0; b < CC; ++b) {
+                double d0 = __dsub_rn(x.x, cx[b]), d1 = __dsub_rn(x.y, cx[b]);
+                ax[b] = __dmul_rn(d0, d0);
+                bx[b] = __dmul_rn(d1, d1);
+            }
+            if constexpr (YSP > 0) {
+#pragma unroll
+                for (int a = 0; a < CR; a += 2) {
+                    const double2 u = *reinterpret_cast<const double2 *>(yq + a), v = *reinterpret_cast<const double2 *>(yq + H + a);
+                    ay[a] = u.x; ay[a + 1] = u.y;
+                    by[a] = v.x; by[a + 1] = v.y;
+                }
+                yq += 2 * H;
+            } else {
+                const double2 y = *reinterpret_cast<const double2 *>(sy + i);
+#pragma unroll
+                for (int a = 0; a < CR; ++a) {
+                    double d0 = __dsub_rn(y.x, cy[a]), d1 = __dsub_rn(y.y, cy[a]);
+                    ay[a] = __dmul_rn(d0, d0);
+                    by[a] = __dmul_rn(d1, d1);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < CR; ++a)
+#pragma unroll
+                for (int b = 0; b < CC; ++b) {
+                    const double A = __dadd_rn(ax[b], ay[a]), B = __dadd_rn(bx[b], by[a]);
+                    const double r = pow_m1(A * B);
+                    const double N = fma(w.x, B, w.y * A);
+                    double &num = acc[(a * CC + b) * 2], &den = acc[(a * CC + b) * 2 + 1];
+                    num = fma(N, r, num);
+                    den = fma(A + B, r, den);
+                }
+        }
+    }
+
     __device__ __forceinline__ void points(const KParams &p, const double *sx, const double *sy, const double *sw, int cnt,
                                            Ctrl *ctrl, unsigned it) {
-        int i = 0;
+        bool paired_ok = false;
         if constexpr (PAIRED) {
             static_assert(MODE == MODE_RCP && E == 1 && K0 == 1, "pairing is the p = 2 trick");
             const int slot = it & 1;
             bool unsafe = false;
-            const TileBox box = tile_box<32 * CC, WARPS * CR>(p, (long long)tile_c * (32 * CC), p.row0 + (long long)tile_r * (WARPS * CR));
+            const TileBox box = tile_box<32 * CC, H>(p, (long long)tile_c * (32 * CC), p.row0 + (long long)tile_r * H);
             for (int k = threadIdx.x; k < cnt; k += THREADS)
-                unsafe |= pairing_unsafe<32 * CC, WARPS * CR>(sx[k], sy[k], p, box, 0x1p-250, 0x1p+249);
+                unsafe |= pairing_unsafe<32 * CC, H>(sx[k], sy[k], p, box, 0x1p-250, 0x1p+249);
             if (unsafe) ctrl->guard[slot] = 1;
             __syncthreads();
-            const bool paired_ok = !ctrl->guard[slot];
+            paired_ok = !ctrl->guard[slot];
             if (threadIdx.x == 0) ctrl->guard[slot ^ 1] = 0;  // nobody touches the other slot until the next tile
-            if constexpr (PAIRED == 2) {
-                constexpr int H = WARPS * CR;  // rows of the CTA tile
-                static_assert(H == 32, "one lane per tile row in the staging pass");
-                if (paired_ok) {
-                    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-                    // this lane's row in the staging pass (RCToPoint, tools/utils.go:78-82)
-                    const double cyr = __dadd_rn(p.y_min, __dmul_rn((double)(p.row0 + (long long)tile_r * H + lane), p.y_step));
-                    const int even = cnt & ~1;
-                    for (int h0 = 0; h0 < even; h0 += YS_POINTS) {
-                        const int hn = min(YS_POINTS, even - h0);
-                        if (h0) __syncthreads();  // the previous half has been consumed
-                        for (int k = warp; k < hn; k += WARPS) {
-                            const double d = __dsub_rn(sy[h0 + k], cyr);
-                            ys[k * H + lane] = __dmul_rn(d, d);
-                        }
-                        __syncthreads();
-                        const double2 *yq = reinterpret_cast<const double2 *>(ys + warp * CR);
-#pragma unroll 1
-                        for (i = h0; i < h0 + hn; i += 2, yq += H) {
-                            const double2 x = *reinterpret_cast<const double2 *>(sx + i);
-                            const double2 w = *reinterpret_cast<const double2 *>(sw + i);
-                            double ax[CC], bx[CC], ay[CR], by[CR];
-#pragma unroll
-                            for (int b = 0; b < CC; ++b) {
-                                double d0 = __dsub_rn(x.x, cx[b]), d1 = __dsub_rn(x.y, cx[b]);
-                                ax[b] = __dmul_rn(d0, d0);
-                                bx[b] = __dmul_rn(d1, d1);
-                            }
-#pragma unroll
-                            for (int a = 0; a < CR; a += 2) {
-                                const double2 u = yq[a / 2], v = yq[H / 2 + a / 2];
-                                ay[a] = u.x; ay[a + 1] = u.y;
-                                by[a] = v.x; by[a + 1] = v.y;
-                            }
-#pragma unroll
-                            for (int a = 0; a < CR; ++a)
-#pragma unroll
-                                for (int b = 0; b < CC; ++b) {
-                                    const double A = __dadd_rn(ax[b], ay[a]), B = __dadd_rn(bx[b], by[a]);
-                                    const double r = pow_m1(A * B);
-                                    const double N = fma(w.x, B, w.y * A);
-                                    double &num = acc[(a * CC + b) * 2], &den = acc[(a * CC + b) * 2 + 1];
-                                    num = fma(N, r, num);
-                                    den = fma(A + B, r, den);
-                                }
-                        }
-                    }
-                    i = even;
+        }
+        if constexpr (YSP > 0) {
+            const int srow = threadIdx.x % H, sfirst = threadIdx.x / H;
+            // this thread's row in the staging pass (RCToPoint, tools/utils.go:78-82)
+            const double cyr = __dadd_rn(p.y_min, __dmul_rn((double)(p.row0 + (long long)tile_r * H + srow), p.y_step));
+            const double *yq = ys + (threadIdx.x >> 5) * CR;
+            for (int h0 = 0; h0 < cnt; h0 += YSP) {
+                const int hn = min(YSP, cnt - h0);
+                if (h0) __syncthreads();  // the previous chunk has been consumed
+                for (int k = sfirst; k < hn; k += THREADS / H) {
+                    const double d = __dsub_rn(sy[h0 + k], cyr);
+                    ys[k * H + srow] = __dmul_rn(d, d);
                 }
-            } else if (paired_ok) {
-#pragma unroll 1
-                for (; i + 1 < cnt; i += 2) {
-                    const double2 x = *reinterpret_cast<const double2 *>(sx + i);
-                    const double2 y = *reinterpret_cast<const double2 *>(sy + i);
-                    const double2 w = *reinterpret_cast<const double2 *>(sw + i);
-                    double ax[CC], bx[CC], ay[CR], by[CR];
-#pragma unroll
-                    for (int b = 0; b < CC; ++b) {
-                        double d0 = __dsub_rn(x.x, cx[b]), d1 = __dsub_rn(x.y, cx[b]);
-                        ax[b] = __dmul_rn(d0, d0);
-                        bx[b] = __dmul_rn(d1, d1);
+                __syncthreads();
+                int i = h0;
+                if constexpr (PAIRED) {
+                    if (paired_ok) {
+                        paired_points(sx, sy, sw, h0, h0 + (hn & ~1), yq);
+                        i = h0 + (hn & ~1);
                     }
-#pragma unroll
-                    for (int a = 0; a < CR; ++a) {
-                        double d0 = __dsub_rn(y.x, cy[a]), d1 = __dsub_rn(y.y, cy[a]);
-                        ay[a] = __dmul_rn(d0, d0);
-                        by[a] = __dmul_rn(d1, d1);
-                    }
-#pragma unroll
-                    for (int a = 0; a < CR; ++a)
-#pragma unroll
-                        for (int b = 0; b < CC; ++b) {
-                            const double A = __dadd_rn(ax[b], ay[a]), B = __dadd_rn(bx[b], by[a]);
-                            const double r = pow_m1(A * B);
-                            const double N = fma(w.x, B, w.y * A);
-                            double &num = acc[(a * CC + b) * 2], &den = acc[(a * CC + b) * 2 + 1];
-                            num = fma(N, r, num);
-                            den = fma(A + B, r, den);
-                        }
+                }
+                single_points(p, sx, sy, sw, i, h0 + hn, yq + (long long)(i - h0) * H);
+            }
+        } else {
+            int i = 0;
+            if constexpr (PAIRED) {
+                if (paired_ok) {
+                    paired_points(sx, sy, sw, 0, cnt & ~1, nullptr);
+                    i = cnt & ~1;
                 }
             }
+            single_points(p, sx, sy, sw, i, cnt, nullptr);
         }
-        single_points(p, sx, sy, sw, i, cnt);
     }
 
     __device__ __forceinline__ void store(const KParams &p) {
@@ -590,10 +612,14 @@ struct Fp64Body {
     }
 };
 
-template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS, int MINB, int PAIRED = 0>
+// OPT: bit 0 = paired reciprocal (p = 2), bit 1 = dy^2 staged in shared memory
+template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS, int MINB, int OPT>
+using Fp64BodyFor = Fp64Body<MODE, E, CR, CC, K0, DK, THREADS, (OPT & 1) != 0, (OPT & 2) ? ys_points(MODE, E, CR, CC, THREADS, MINB) : 0>;
+
+template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS, int MINB, int OPT = 0>
 __global__ void __launch_bounds__(THREADS, MINB) idw_fp64_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    Fp64Body<MODE, E, CR, CC, K0, DK, THREADS, PAIRED> body(p, smem);
+    Fp64BodyFor<MODE, E, CR, CC, K0, DK, THREADS, MINB, OPT> body(p, smem);
     tile_driver(p, body, smem);
 }
 

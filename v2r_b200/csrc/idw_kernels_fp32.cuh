@@ -15,6 +15,8 @@
 //     the cell offsets are small integers, exact in FP32, and need no lo part; y' is scaled back by y_step / x_step
 //     when the steps differ.  Weights then carry a constant factor x_step^2 that cancels in num / den;
 //   - per-point values are stored duplicated (v, v) in shared memory, so one LDS.64 delivers a two-wide operand;
+//   - the squared ROW distances depend on (point, tile row) only: the CTA computes them once per chunk of points into
+//     shared memory, duplicated, instead of every warp recomputing them with half-wasted two-wide instructions;
 //   - two points still share ONE MUFU.RCP: 1/a + 1/b = (a+b)/(ab), w0/a + w1/b = (w0 b + w1 a)/(ab);
 //     per two cells x two points: 8 packed instructions + 2 MUFU (round 1: 18 scalar + 2 MUFU).
 //   A point tile that is not safe for pairing on this CTA's cells (a*b could leave the FP32 normal range: distances
@@ -211,56 +213,70 @@ __global__ void __launch_bounds__(THREADS, MINB) idw_fp32_kernel(const __grid_co
 // ---------------------------------------------------------------------------- packed body (p = 2)
 __device__ __forceinline__ float2 f2dup(float v) { return make_float2(v, v); }
 
-template <int CR, int CC, bool ISO, int THREADS_>
+// points per staged chunk of squared row distances ((v, v) float2 per point and tile row): fits MINB CTAs per SM
+__host__ __device__ constexpr int ys32_points(int CR, int CC, int threads, int minb) {
+    const int rows = (threads / 32) * CR;
+    const int fixed = kStageBytes + kCtrlBytes + 5 * kTilePoints * 8 + 2 * CR * CC * threads * 8;
+    const int budget = (227 * 1024) / minb - 1024;
+    for (int pts = 256; pts >= 32; pts /= 2)
+        if (fixed + pts * rows * 8 <= budget) return pts;
+    return 0;
+}
+
+template <int CR, int CC, bool ISO, int THREADS_, int YSP>
 struct Fp32PackedBody {
     static_assert(CC % 2 == 0, "columns are processed in pairs");
+    static_assert(YSP > 0 && YSP % 2 == 0, "the squared row distances are staged in shared memory");
     static constexpr int THREADS = THREADS_;
     static constexpr int WARPS = THREADS / 32;
     static constexpr int CP = CC / 2;                 // column pairs per thread
     static constexpr int NACC = 2 * CR * CC;          // acc[(a*CC + b)*2 + {0: num, 1: den}]
     static constexpr int T = kTilePoints;
-    static constexpr int BODY_BYTES = 5 * T * (int)sizeof(float2);  // (v, v) pairs: x hi, x lo, y hi, y lo, w
     static constexpr int W = 32 * CC, H = WARPS * CR; // CTA tile in cells
+    static_assert(THREADS % H == 0, "staging layout");
+    // (v, v) pairs: x hi, x lo, w; y hi / lo as plain floats (only the staging pass reads them); staged dy^2 chunk
+    static constexpr int BODY_BYTES = 3 * T * (int)sizeof(float2) + 2 * T * (int)sizeof(float) + YSP * H * (int)sizeof(float2);
 
     double acc[NACC];
     float2 nkx[CP];   // minus the column offsets (cells from the tile centre) of columns (2j, 2j+1)
-    float2 nky[CR];   // minus the row offset, duplicated
     int tile_r, tile_c;
     double ox, oy;    // centre node of the CTA tile
-    float2 *fxh, *fxl, *fyh, *fyl, *fw;
+    float2 *fxh, *fxl, *fw, *ys;
+    float *fyh, *fyl;
 
     __device__ __forceinline__ Fp32PackedBody(const KParams &, unsigned char *smem) {
         float2 *f = reinterpret_cast<float2 *>(smem + kStageBytes + kCtrlBytes);
-        fxh = f; fxl = f + T; fyh = f + 2 * T; fyl = f + 3 * T; fw = f + 4 * T;
+        fxh = f; fxl = f + T; fw = f + 2 * T;
+        fyh = reinterpret_cast<float *>(f + 3 * T);
+        fyl = fyh + T;
+        ys = reinterpret_cast<float2 *>(fyl + T);
     }
 
     __device__ __forceinline__ void setup(const KParams &p, int tr, int tc) {
         tile_r = tr;
         tile_c = tc;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int lane = threadIdx.x & 31;
         const long long r0 = p.row0 + (long long)tile_r * H, c0 = (long long)tile_c * W;
         ox = __dadd_rn(p.x_min, __dmul_rn((double)(c0 + W / 2), p.x_step));
         oy = __dadd_rn(p.y_min, __dmul_rn((double)(r0 + H / 2), p.y_step));
 #pragma unroll
         for (int j = 0; j < CP; ++j)
             nkx[j] = make_float2(-(float)(lane + 64 * j - W / 2), -(float)(lane + 64 * j + 32 - W / 2));
-#pragma unroll
-        for (int a = 0; a < CR; ++a) nky[a] = f2dup(-(float)(warp * CR + a - H / 2));
     }
 
     __device__ __forceinline__ void points(const KParams &p, const double *sx, const double *sy, const double *sw, int cnt,
                                            Ctrl *ctrl, unsigned it) {
         const int slot = it & 1;
         const double rho = ISO ? 1.0 : p.y_step * p.inv_x_step;  // y cells -> x cells
-        // FP64 tile -> cell units from the tile centre, hi + lo floats, stored duplicated; and the pairing guard
+        // FP64 tile -> cell units from the tile centre, hi + lo floats (x and w stored duplicated); and the pairing guard
         bool unsafe = false;
         for (int i = threadIdx.x; i < cnt; i += THREADS) {
             const double vx = (sx[i] - ox) * p.inv_x_step, vy = (sy[i] - oy) * p.inv_y_step;
             const float hx = (float)vx, hy = (float)vy;
             fxh[i] = f2dup(hx);
             fxl[i] = f2dup((float)(vx - (double)hx));
-            fyh[i] = f2dup(hy);
-            fyl[i] = f2dup((float)(vy - (double)hy));
+            fyh[i] = hy;
+            fyl[i] = (float)(vy - (double)hy);
             fw[i] = f2dup((float)sw[i]);
             // nearest / farthest cell of the tile along each axis (cells sit at the integers -W/2 .. W/2-1)
             const double kx = fmin(fmax(rint(vx), -(double)(W / 2)), (double)(W / 2 - 1));
@@ -274,7 +290,6 @@ struct Fp32PackedBody {
         __syncthreads();
         const bool paired_ok = !ctrl->guard[slot];
         if (threadIdx.x == 0) ctrl->guard[slot ^ 1] = 0;
-        const float2 rho2 = f2dup((float)rho);
 
         float2 pn[CR][CP], pd[CR][CP];
 #pragma unroll
@@ -282,65 +297,67 @@ struct Fp32PackedBody {
 #pragma unroll
             for (int j = 0; j < CP; ++j) { pn[a][j] = make_float2(0.f, 0.f); pd[a][j] = make_float2(0.f, 0.f); }
 
-        // squared row distance (duplicated) and column distance (two columns) of one point
-        auto row_sq = [&](float2 yh, float2 yl, int a) {
-            float2 d = __fadd2_rn(__fadd2_rn(yh, nky[a]), yl);
-            if constexpr (!ISO) d = __fmul2_rn(d, rho2);
-            return __fmul2_rn(d, d);
-        };
         auto col_d = [&](float2 xh, float2 xl, int j) { return __fadd2_rn(__fadd2_rn(xh, nkx[j]), xl); };
+        // staging pass: this thread's tile row (cells from the centre) and the squared row distance, duplicated
+        const int srow = threadIdx.x % H, sfirst = threadIdx.x / H;
+        const float nrow = -(float)(srow - H / 2), frho = (float)rho;
+        const float2 *yq0 = ys + (threadIdx.x >> 5) * CR;
 
-        int i = 0;
-        if (paired_ok) {
+        for (int h0 = 0; h0 < cnt; h0 += YSP) {
+            const int hn = min(YSP, cnt - h0);
+            if (h0) __syncthreads();  // the previous chunk has been consumed
+            for (int k = sfirst; k < hn; k += THREADS / H) {
+                float d = (fyh[h0 + k] + nrow) + fyl[h0 + k];
+                if constexpr (!ISO) d *= frho;
+                ys[k * H + srow] = f2dup(d * d);
+            }
+            __syncthreads();
+            const float2 *yq = yq0;
+            int i = h0;
+            if (paired_ok) {
 #pragma unroll 1
-            for (; i + 1 < cnt; i += 2) {
-                const float4 xh = *reinterpret_cast<const float4 *>(fxh + i), xl = *reinterpret_cast<const float4 *>(fxl + i);
-                const float4 yh = *reinterpret_cast<const float4 *>(fyh + i), yl = *reinterpret_cast<const float4 *>(fyl + i);
-                const float4 w = *reinterpret_cast<const float4 *>(fw + i);
-                const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
-                float2 dx0[CP], dx1[CP], ay[CR], by[CR];
-#pragma unroll
-                for (int j = 0; j < CP; ++j) {
-                    dx0[j] = col_d(make_float2(xh.x, xh.y), make_float2(xl.x, xl.y), j);
-                    dx1[j] = col_d(make_float2(xh.z, xh.w), make_float2(xl.z, xl.w), j);
-                }
-#pragma unroll
-                for (int a = 0; a < CR; ++a) {
-                    ay[a] = row_sq(make_float2(yh.x, yh.y), make_float2(yl.x, yl.y), a);
-                    by[a] = row_sq(make_float2(yh.z, yh.w), make_float2(yl.z, yl.w), a);
-                }
-#pragma unroll
-                for (int a = 0; a < CR; ++a)
+                for (; i + 1 < h0 + hn; i += 2, yq += 2 * H) {
+                    const float4 xh = *reinterpret_cast<const float4 *>(fxh + i), xl = *reinterpret_cast<const float4 *>(fxl + i);
+                    const float4 w = *reinterpret_cast<const float4 *>(fw + i);
+                    const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
+                    float2 dx0[CP], dx1[CP];
 #pragma unroll
                     for (int j = 0; j < CP; ++j) {
-                        const float2 A = __ffma2_rn(dx0[j], dx0[j], ay[a]), B = __ffma2_rn(dx1[j], dx1[j], by[a]);
-                        const float2 P = __fmul2_rn(A, B);
-                        const float2 r = make_float2(frcp(P.x), frcp(P.y));
-                        const float2 N = __ffma2_rn(w0, B, __fmul2_rn(w1, A));
-                        pn[a][j] = __ffma2_rn(N, r, pn[a][j]);
-                        pd[a][j] = __ffma2_rn(__fadd2_rn(A, B), r, pd[a][j]);
+                        dx0[j] = col_d(make_float2(xh.x, xh.y), make_float2(xl.x, xl.y), j);
+                        dx1[j] = col_d(make_float2(xh.z, xh.w), make_float2(xl.z, xl.w), j);
                     }
+#pragma unroll
+                    for (int a = 0; a < CR; ++a) {
+                        const float2 ay = yq[a], by = yq[H + a];
+#pragma unroll
+                        for (int j = 0; j < CP; ++j) {
+                            const float2 A = __ffma2_rn(dx0[j], dx0[j], ay), B = __ffma2_rn(dx1[j], dx1[j], by);
+                            const float2 P = __fmul2_rn(A, B);
+                            const float2 r = make_float2(frcp(P.x), frcp(P.y));
+                            const float2 N = __ffma2_rn(w0, B, __fmul2_rn(w1, A));
+                            pn[a][j] = __ffma2_rn(N, r, pn[a][j]);
+                            pd[a][j] = __ffma2_rn(__fadd2_rn(A, B), r, pd[a][j]);
+                        }
+                    }
+                }
             }
-        }
 #pragma unroll 1
-        for (; i < cnt; ++i) {  // one reciprocal per pair: odd tail, or a tile that is not safe for pairing
-            const float2 xh = fxh[i], xl = fxl[i], yh = fyh[i], yl = fyl[i], w = fw[i];
-            float2 ay[CR];
+            for (; i < h0 + hn; ++i, yq += H) {  // one reciprocal per pair: odd tail, or a tile that is not safe for pairing
+                const float2 xh = fxh[i], xl = fxl[i], w = fw[i];
 #pragma unroll
-            for (int a = 0; a < CR; ++a) ay[a] = row_sq(yh, yl, a);
+                for (int j = 0; j < CP; ++j) {
+                    const float2 dx = col_d(xh, xl, j);
 #pragma unroll
-            for (int j = 0; j < CP; ++j) {
-                const float2 dx = col_d(xh, xl, j);
-#pragma unroll
-                for (int a = 0; a < CR; ++a) {
-                    float2 A = __ffma2_rn(dx, dx, ay[a]);
-                    // cell units lose offsets below ~1e-14 cells: a point that close (but not ON the node -- those cells
-                    // are poisoned afterwards) must still dominate its cell with a finite weight; NaN passes through
-                    A.x = A.x < 0x1p-60f ? 0x1p-60f : A.x;
-                    A.y = A.y < 0x1p-60f ? 0x1p-60f : A.y;
-                    const float2 r = make_float2(frcp(A.x), frcp(A.y));
-                    pn[a][j] = __ffma2_rn(w, r, pn[a][j]);
-                    pd[a][j] = __fadd2_rn(pd[a][j], r);
+                    for (int a = 0; a < CR; ++a) {
+                        float2 A = __ffma2_rn(dx, dx, yq[a]);
+                        // cell units lose offsets below ~1e-14 cells: a point that close (but not ON the node -- those
+                        // cells are poisoned afterwards) must still dominate its cell with a finite weight; NaN passes
+                        A.x = A.x < 0x1p-60f ? 0x1p-60f : A.x;
+                        A.y = A.y < 0x1p-60f ? 0x1p-60f : A.y;
+                        const float2 r = make_float2(frcp(A.x), frcp(A.y));
+                        pn[a][j] = __ffma2_rn(w, r, pn[a][j]);
+                        pd[a][j] = __fadd2_rn(pd[a][j], r);
+                    }
                 }
             }
         }
@@ -375,9 +392,12 @@ struct Fp32PackedBody {
 };
 
 template <int CR, int CC, bool ISO, int THREADS, int MINB>
+using Fp32PackedBodyFor = Fp32PackedBody<CR, CC, ISO, THREADS, ys32_points(CR, CC, THREADS, MINB)>;
+
+template <int CR, int CC, bool ISO, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) idw_fp32_packed_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    Fp32PackedBody<CR, CC, ISO, THREADS> body(p, smem);
+    Fp32PackedBodyFor<CR, CC, ISO, THREADS, MINB> body(p, smem);
     tile_driver(p, body, smem);
 }
 

@@ -103,21 +103,19 @@ struct Variant {
     bool paired;
     const char *tag;  // non-null: tuning build, selected only by V2R_IDW_TUNE=<tag>
     int smem;         // dynamic shared memory per CTA
+    int opt;          // bit 0 = paired reciprocal, bit 1 = dy^2 staged in shared memory
 };
 
-#define V2R_SMEM(MODE, E, CR, CC, THREADS) smem_bytes((MODE) == MODE_GEN ? (int)sizeof(GenTables) : 0, 2 * (E) * (CR) * (CC), THREADS)
-#define V2R_PAIRED_YS(TAG, CR, CC, THREADS, MINB)                                                                                     \
-    Variant { MODE_RCP, 1, 1, 0, CR, CC, THREADS, idw_fp64_kernel<MODE_RCP, 1, CR, CC, 1, 0, THREADS, MINB, 2>, "MODE_RCP", true, TAG, \
-              smem_bytes(Fp64Body<MODE_RCP, 1, CR, CC, 1, 0, THREADS, 2>::BODY_BYTES, 2 * (CR) * (CC), THREADS) }
-#define V2R_VARIANT(MODE, E, CR, CC, K0, DK, THREADS, MINB)                                                                     \
-    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE, false, nullptr, \
-              V2R_SMEM(MODE, E, CR, CC, THREADS) }
-#define V2R_TUNE(TAG, MODE, E, CR, CC, K0, DK, THREADS, MINB)                                                               \
-    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB>, #MODE, false, TAG, \
-              V2R_SMEM(MODE, E, CR, CC, THREADS) }
-#define V2R_PAIRED(TAG, CR, CC, THREADS, MINB)                                                                                    \
-    Variant { MODE_RCP, 1, 1, 0, CR, CC, THREADS, idw_fp64_kernel<MODE_RCP, 1, CR, CC, 1, 0, THREADS, MINB, 1>, "MODE_RCP", true, TAG, \
-              V2R_SMEM(MODE_RCP, 1, CR, CC, THREADS) }
+// OPT of the kernels: bit 0 = paired reciprocal, bit 1 = dy^2 staged in shared memory (idw_kernels.cuh)
+#define V2R_KERNEL(MODE, E, CR, CC, K0, DK, THREADS, MINB, OPT, PAIRED, TAG)                                              \
+    Variant { MODE, E, K0, DK, CR, CC, THREADS, idw_fp64_kernel<MODE, E, CR, CC, K0, DK, THREADS, MINB, OPT>, #MODE, PAIRED, TAG, \
+              smem_bytes(Fp64BodyFor<MODE, E, CR, CC, K0, DK, THREADS, MINB, OPT>::BODY_BYTES, 2 * (E) * (CR) * (CC), THREADS), OPT }
+#define V2R_VARIANT(MODE, E, CR, CC, K0, DK, THREADS, MINB) V2R_KERNEL(MODE, E, CR, CC, K0, DK, THREADS, MINB, kStage, false, nullptr)
+#define V2R_TUNE(TAG, MODE, E, CR, CC, K0, DK, THREADS, MINB) V2R_KERNEL(MODE, E, CR, CC, K0, DK, THREADS, MINB, kStage, false, TAG)
+#define V2R_UNSTAGED(TAG, MODE, E, CR, CC, K0, DK, THREADS, MINB) V2R_KERNEL(MODE, E, CR, CC, K0, DK, THREADS, MINB, 0, false, TAG)
+#define V2R_PAIRED(TAG, CR, CC, THREADS, MINB) V2R_KERNEL(MODE_RCP, 1, CR, CC, 1, 0, THREADS, MINB, 1, true, TAG)
+#define V2R_PAIRED_YS(TAG, CR, CC, THREADS, MINB) V2R_KERNEL(MODE_RCP, 1, CR, CC, 1, 0, THREADS, MINB, 3, true, TAG)
+constexpr int kStage = 2;
 
 // Cell block per thread shrinks as E grows (2*E*CR*CC FP64 accumulators live in registers).
 #define V2R_ROW(MODE)                                                                                  \
@@ -140,6 +138,9 @@ static const Variant kVariants[] = {
     V2R_TUNE("g4x2", MODE_GEN, 1, 4, 2, GEN_SINGLE, 0, 256, 2),
     V2R_PAIRED("c4x6", 4, 6, 256, 1), V2R_PAIRED_YS("ys4x6", 4, 6, 256, 1),
     V2R_PAIRED("nys", 4, 4, 256, 1),                // p = 2, paired, every lane computes its own dy^2 (round 1's loop)
+    V2R_UNSTAGED("nys", MODE_RSQ, 1, 2, 4, 1, 0, 256, 2), V2R_UNSTAGED("nys", MODE_QRT, 1, 2, 4, 3, 0, 256, 2),
+    V2R_UNSTAGED("nys", MODE_QRT, 9, 2, 2, 1, 1, 256, 1), V2R_UNSTAGED("nys", MODE_QRT, 4, 2, 2, 2, 1, 256, 2),
+    V2R_UNSTAGED("nys", MODE_GEN, 1, 2, 4, GEN_SINGLE, 0, 256, 2), V2R_UNSTAGED("nys", MODE_GEN, 4, 2, 2, GEN_SINGLE, 0, 256, 2),
     // compile-time ladders for the headline shapes (looked up first)
     V2R_PAIRED_YS(nullptr, 4, 4, 256, 1),           // p = 2, paired, dy^2 staged in shared memory once per CTA (c2, c4)
     V2R_VARIANT(MODE_RCP, 1, 4, 4, 1, 0, 256, 1),   // p = 2, one reciprocal per pair (V2R_IDW_FP64_PAIRED=0)
@@ -192,6 +193,7 @@ static const char *mode_name(int m) {
 static double model_ops(const Pass &ps, const Variant &v) {
     const int E = ps.count;
     double per_point = 2.0 * (v.cr + v.cc) / double(v.cr * v.cc);  // dx, dx^2, dy, dy^2 amortised
+    if (v.opt & 2) per_point = 2.0 / v.cr;                          // dy, dy^2 come from shared memory (once per CTA)
     double ops = per_point + 1.0 /* d2 */ + 2.0 * E /* fma + add */;
     auto ladder = [](int k) {  // multiplies of square-and-multiply
         int m = 0, hi = 0;
@@ -206,8 +208,6 @@ static double model_ops(const Pass &ps, const Variant &v) {
     } else {
         ops += ps.mode == MODE_RCP ? 3 : (ps.mode == MODE_RSQ ? 5 : 7);
         if (v.paired) ops -= 0.5;  // 11 instead of 12 instructions per two pairs
-        if (v.paired && v.fn == (void (*)(const KParams))idw_fp64_kernel<MODE_RCP, 1, 4, 4, 1, 0, 256, 1, 2>)
-            ops -= 2.0 / v.cc;     // dy, dy^2 come from shared memory (computed once per CTA, not per lane)
         ops += ladder(ps.k0);
         if (E > 1) ops += ladder(ps.dk) + (E - 1);
     }

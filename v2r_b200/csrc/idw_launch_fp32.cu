@@ -24,7 +24,7 @@ struct FVariant {
                smem_bytes(Fp32Body<MODE, E, CR, CC, 256>::BODY_BYTES, 2 * (E) * (CR) * (CC), 256), nullptr }
 #define V2R_FPACKED(TAG, CR, CC, ISO, THREADS, MINB)                                                                  \
     FVariant { MODE_RCP, 1, true, ISO, CR, CC, THREADS, MINB, idw_fp32_packed_kernel<CR, CC, ISO, THREADS, MINB>,     \
-               smem_bytes(Fp32PackedBody<CR, CC, ISO, THREADS>::BODY_BYTES, 2 * (CR) * (CC), THREADS), TAG }
+               smem_bytes(Fp32PackedBodyFor<CR, CC, ISO, THREADS, MINB>::BODY_BYTES, 2 * (CR) * (CC), THREADS), TAG }
 #define V2R_FROW(MODE)                                                                          \
     V2R_FVARIANT(MODE, 1, 4, 4, 2), V2R_FVARIANT(MODE, 2, 2, 4, 2),                             \
         V2R_FVARIANT(MODE, 3, 2, 2, 2), V2R_FVARIANT(MODE, 4, 2, 2, 2),                         \
