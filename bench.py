@@ -352,10 +352,10 @@ def ours(args):
                 "kernel": kernel, "ms_per_launch": ms_total / args.steps, "measured_peaks_ginst_s": peaks,
             }
         else:
-            # FP32 path: the packed p = 2 kernel (4x8 cells) occupies 5.25 FP32-pipe lane slots per pair (336 per 2 points
-            # x 32 cells: 168 two-wide instructions); the bound is the FP32 pipe (FFMA rate), MUFU
-            # needs half a reciprocal per pair
-            fp32_slots = 5.25
+            # FP32 path: the packed p = 2 kernel (4x4 cells, staged row distances) occupies 4.5 FP32-pipe lane slots per
+            # pair (144 per 2 points x 16 cells: 72 two-wide instructions); the bound is the FP32
+            # pipe (FFMA rate), MUFU needs half a reciprocal per pair
+            fp32_slots = 4.5
             achieved_tflops = per_gpu_pairs_s * fp32_slots / 1e12
             peak_tflops = ffma.value / 1e3
             roofline = {

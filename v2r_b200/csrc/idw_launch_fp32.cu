@@ -34,10 +34,10 @@ struct FVariant {
 
 static const FVariant kFVariants[] = {
     // tuning builds of the packed p = 2 kernel (cell block, CTAs per SM)
-    V2R_FPACKED("f4x4", 4, 4, true, 256, 1), V2R_FPACKED("f2x8", 2, 8, true, 256, 1), V2R_FPACKED("f2x16", 2, 16, true, 256, 1),
-    // p = 2: packed FP32 (FFMA2 / FADD2 / FMUL2), two points per MUFU.RCP; 4x8 cells measured 5 009 G evals/s on c2
-    // against 4 733 (2x8), 4 935 (2x16) and 4 598 (4x4)
-    V2R_FPACKED(nullptr, 4, 8, true, 256, 1), V2R_FPACKED(nullptr, 4, 8, false, 256, 1),
+    V2R_FPACKED("f4x8", 4, 8, true, 256, 1), V2R_FPACKED("f2x8", 2, 8, true, 256, 1), V2R_FPACKED("f2x16", 2, 16, true, 256, 1),
+    // p = 2: packed FP32 (FFMA2 / FADD2 / FMUL2), two points per MUFU.RCP, squared row distances staged in shared
+    // memory; 4x4 cells measured 5 604 G evals/s on c2 against 5 383 (4x8), 5 379 (2x8) and 5 082 (2x16)
+    V2R_FPACKED(nullptr, 4, 4, true, 256, 1), V2R_FPACKED(nullptr, 4, 4, false, 256, 1),
     V2R_FROW(MODE_RCP), V2R_FROW(MODE_RSQ), V2R_FROW(MODE_QRT), V2R_FROW(MODE_GEN),
 };
 
