@@ -5,8 +5,10 @@
 #   tests     pytest -m gpu
 #   classes   one bench line per exponent class / workload (diagnostic bands) + the default bench
 #   tail      short c4 bands with and without the tail split (V2R_IDW_TAIL=0)
-#   ncu       --set full capture per kernel class, FP64-pipe active vs elapsed on short bands, launch list of the bench
-#   multi     (gpurun --gpus N) multi-GPU tests + the default bench and the c2 weak bench under torchrun
+#   ncu       --set full capture per kernel class (summarised on the box)
+#   ncu-lite  metrics-only: FP64-pipe active vs elapsed + DRAM bytes on short bands and the default launch, launch list of the bench
+#   multi     (gpurun --gpus N) multi-GPU tests, c2 weak (direct and NCCL-gather copy-out) and the default bench under
+#             torchrun; `multi <tag> quick` runs the default bench only
 #   tune      tuning builds (cell blocks, staged dy^2) against the default kernels
 #   stream    streaming API against one whole-grid solve (scripts/stream_timing.py) and the CLI on c2 / c5-shaped inputs
 suite=${1:-tests}
@@ -57,6 +59,8 @@ ncu)
     prof fp64_c5_e4_band16 idw_fp64 --workload c5 --band-rows 16
     prof fp64_rsqrt_p1_band512 idw_fp64 --workload c2 --exps 1.0 --band-rows 512
     prof fp64_root4_p15_band512 idw_fp64 --workload c2 --exps 1.5 --band-rows 512
+    ls -la ${O}_*metrics.json ;;
+ncu-lite)   # metrics-only passes: FP64 pipe active vs elapsed + DRAM bytes on short bands and the default launch, launch list
     M=sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed,gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
     for rows in 128 256 2048; do
         python bench.py --steps 1 --warmup 3 $Q --slab 7168:$rows > ${O}_plain_tail$rows.log 2>&1 &&
@@ -66,22 +70,25 @@ ncu)
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --parity-cells 200 > ${O}_plain_launches.log 2>&1 &&
     ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file ${O}_launches_default.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --parity-cells 200 > ${O}_ncu_launches.log 2>&1
     echo "launches rc=$?"
-    ls -la gpurun_out/*.ncu-rep ${O}_*.csv ;;
+    python scripts/ncu_traffic.py ${O}_tail_c4_rows2048.csv 2048 16384 967142 > ${O}_traffic.log 2>&1; cat ${O}_traffic.log
+    cp profiles/traffic.json ${O}_traffic.json
+    ls -la ${O}_*.csv ;;
 multi)
     n=$(nvidia-smi -L | wc -l)
-    timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > ${O}_pytest_multi.log 2>&1; tail -4 ${O}_pytest_multi.log
     T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29541"
-    $T bench.py --gpus $n --steps 5 --warmup 3 --no-cpu-baseline > ${O}_m${n}_default.json 2> ${O}_m${n}.err
-    $T bench.py --gpus $n --steps 5 --warmup 3 --no-cpu-baseline --workload c2 --scaling weak > ${O}_m${n}_c2_weak.json 2>> ${O}_m${n}.err
-    V2R_IDW_GATHER=nccl $T bench.py --gpus $n --steps 2 --warmup 3 --no-cpu-baseline --workload c2 --scaling weak > ${O}_m${n}_c2_weak_ncclgather.json 2>> ${O}_m${n}.err
-    $T bench.py --gpus $n --steps 3 --warmup 3 --no-cpu-baseline --precision fp32 > ${O}_m${n}_default_fp32.json 2>> ${O}_m${n}.err
+    if [ "${3:-full}" = "full" ]; then
+        timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > ${O}_pytest_multi.log 2>&1; tail -4 ${O}_pytest_multi.log
+        $T bench.py --gpus $n --steps 3 --warmup 3 --no-cpu-baseline --workload c2 --scaling weak > ${O}_m${n}_c2_weak.json 2> ${O}_m${n}.err
+        V2R_IDW_GATHER=nccl $T bench.py --gpus $n --steps 2 --warmup 3 --no-cpu-baseline --workload c2 --scaling weak > ${O}_m${n}_c2_weak_ncclgather.json 2>> ${O}_m${n}.err
+    fi
+    $T bench.py --gpus $n --steps 3 --warmup 3 --no-cpu-baseline > ${O}_m${n}_default.json 2>> ${O}_m${n}.err
     tail -3 ${O}_m${n}.err; summ ${O}_m${n}_*.json
     python - <<P
 import json, glob
 for f in sorted(glob.glob("${O}_m${n}_*.json")):
     try:
         d = json.loads([l for l in open(f) if l.startswith("{")][-1])
-        print(f, json.dumps({"e2e": d["e2e"], "parity": d["parity"]})[:900])
+        print(f, json.dumps({"e2e": d["e2e"], "parity": d["parity"]})[:1200])
     except Exception as e:
         print(f, "unreadable", e)
 P

@@ -109,6 +109,7 @@ struct DeviceState {
     cudaEvent_t drained[2] = {nullptr, nullptr};   // buffer b has been copied out / sent: it may be overwritten
     bool drained_valid[2] = {false, false};
     cudaEvent_t k_first = nullptr, k_last = nullptr, c_first = nullptr, c_last = nullptr, up_start = nullptr, up_stop = nullptr;
+    cudaEvent_t h2d_done = nullptr;  // the caller's host arrays have been read completely
     bool k_any = false, c_any = false;
     ncclComm_t comm = nullptr;
     long long band_row0 = 0, band_rows = 0;  // rows owned in the current session
@@ -120,7 +121,8 @@ struct Session {
     long long row0 = 0, nrows = 0;  // requested row range
     std::vector<double> exps;
     int precision = 0;
-    long long sub_rows = 0;   // rows per device per round = one kernel launch (the launch granule)
+    long long sub_rows = 0;   // largest number of rows per device per round (a round = one kernel launch per device)
+    std::vector<long long> round_off;  // round k covers rows [round_off[k], round_off[k+1]) of every device's band
     long long slice_rows = 0; // rows handed to the caller per _next call (<= sub_rows): the write granule
     long long slice_off = 0;  // rows of the current (round, device) band already delivered
     long long rounds = 0;
@@ -150,7 +152,7 @@ static void free_device_state(DeviceState &d) {
     if (d.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d.comm);
     for (void *p : {(void *)d.d_pts, (void *)d.d_band[0], (void *)d.d_band[1]})
         if (p) cudaFree(p);
-    for (cudaEvent_t e : {d.k_stop[0], d.k_stop[1], d.drained[0], d.drained[1], d.k_first, d.k_last, d.c_first, d.c_last, d.up_start, d.up_stop})
+    for (cudaEvent_t e : {d.k_stop[0], d.k_stop[1], d.drained[0], d.drained[1], d.k_first, d.k_last, d.c_first, d.c_last, d.up_start, d.up_stop, d.h2d_done})
         if (e) cudaEventDestroy(e);
     if (d.compute) cudaStreamDestroy(d.compute);
     if (d.copy) cudaStreamDestroy(d.copy);
@@ -166,6 +168,7 @@ static int init_device_state(DeviceState &d, int device) {
         CUDA_TRY(cudaEventCreateWithFlags(&d.drained[i], cudaEventDisableTiming));
     }
     for (cudaEvent_t *e : {&d.k_first, &d.k_last, &d.c_first, &d.c_last, &d.up_start, &d.up_stop}) CUDA_TRY(cudaEventCreate(e));
+    CUDA_TRY(cudaEventCreateWithFlags(&d.h2d_done, cudaEventDisableTiming));
     return V2R_IDW_OK;
 }
 
@@ -266,8 +269,7 @@ static int upload_points(v2r_idw_ctx *ctx, const double *x, const double *y, con
         CUDA_TRY(cudaMemcpyAsync(d0.d_kr, kr, n * 8, cudaMemcpyHostToDevice, d0.compute));
         CUDA_TRY(cudaMemcpyAsync(d0.d_kc, kc, n * 8, cudaMemcpyHostToDevice, d0.compute));
     }
-    cudaEvent_t h2d_done = d0.k_last;  // free at this point of a session; re-recorded by the first kernel round
-    CUDA_TRY(cudaEventRecord(h2d_done, d0.compute));
+    CUDA_TRY(cudaEventRecord(d0.h2d_done, d0.compute));
     if (ctx->dev.size() > 1 && n > 0) {
         NCCL_TRY(g_nccl.GroupStart());  // one collective; the group only spans this process's communicators
         for (auto &d : ctx->dev)
@@ -276,7 +278,7 @@ static int upload_points(v2r_idw_ctx *ctx, const double *x, const double *y, con
     }
     CUDA_TRY(cudaSetDevice(d0.device));
     CUDA_TRY(cudaEventRecord(d0.up_stop, d0.compute));
-    CUDA_TRY(cudaEventSynchronize(h2d_done));  // pinned host arrays make the copies truly asynchronous: wait for the DMA
+    CUDA_TRY(cudaEventSynchronize(d0.h2d_done));  // pinned host arrays make the copies truly asynchronous: wait for the DMA
     return V2R_IDW_OK;
 }
 
@@ -284,8 +286,8 @@ static long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 
 // rows of device g's sub-band in round k, clipped to its band
 static void sub_band(const Session &s, const DeviceState &d, long long k, long long *r0, long long *nr) {
-    long long a = d.band_row0 + k * s.sub_rows;
-    long long e = std::min(a + s.sub_rows, d.band_row0 + d.band_rows);
+    long long a = d.band_row0 + std::min(s.round_off[k], d.band_rows);
+    long long e = d.band_row0 + std::min(s.round_off[k + 1], d.band_rows);
     *r0 = a;
     *nr = e > a ? e - a : 0;
 }
@@ -359,26 +361,44 @@ static int begin_session(v2r_idw_ctx *ctx, const double *x, const double *y, con
         d.k_any = d.c_any = false;
         d.drained_valid[0] = d.drained_valid[1] = false;
     }
-    // Launch granule (rows per device per round).  Every device's band is cut into up to 8 rounds of at least
-    // ~2 M cells and at most ~1 GiB of output, so the copy-out of round k overlaps the kernels of round k+1 and only
-    // the last round's copy is exposed; the kernels keep their efficiency on short bands because the last partial
-    // wave of a launch is shared out by point segments (idw_kernels.cuh).  When the caller asks for small bands
-    // (the reference's default chunk is 200 rows) the granule is a multiple of the requested height.
+    // Launch granule (rows per device per round).  Cutting a device's band into R rounds lets the copy-out of round k
+    // overlap the kernels of round k+1, so only bytes/R of copy is exposed at the end -- but every launch ends with a
+    // tail of about 1/16 of a tile time (idw_kernels.cuh), and a tile costs 4096 cells x n points.  R minimises
+    // R * t_tail + bytes / (R * bw): c2 (100 k points, 134 MB per device) -> 2 rounds; the c4 slab (967 k points:
+    // 14 ms of tail per launch against 13 ms of copy) -> 1 round.  Each round holds at most ~1 GiB of output.  When the
+    // caller asks for small bands (the reference's default chunk is 200 rows) the granule is a multiple of the
+    // requested height.
     const long long cols1 = std::max<long long>(1, grid->cols);
     const long long row_bytes = cols1 * 8 * n_exps;
     const long long cap_rows = std::max<long long>(32, ((1LL << 30) / row_bytes) / 32 * 32);
-    const long long min_rows = std::max<long long>(32, ceil_div(ceil_div(1LL << 21, cols1), 32) * 32);
-    long long sub = std::max(min_rows, ceil_div(ceil_div(per, 8), 32) * 32);
-    sub = std::min(sub, cap_rows);
-    if (band_rows > 0) {
-        const long long k = std::max<long long>(1, std::min(ceil_div(sub, band_rows), std::max<long long>(1, cap_rows / band_rows)));
-        sub = band_rows * k;
+    const double t_tail = 4096.0 * (double)std::max<long long>(n, 1) * 148.0 / estimate_pair_rate(exps, n_exps, precision) / 16.0;
+    const double t_copy = (double)per * (double)row_bytes / 20e9;  // one device's band over its PCIe link
+    long long want_rounds = (long long)std::llround(std::sqrt(t_copy / std::max(t_tail, 1e-6)));
+    want_rounds = std::max<long long>(1, std::min<long long>(want_rounds, 8));
+    // Rounds: want_rounds - 1 equal granules followed by a SHORT last round (about a quarter of a granule): the last
+    // round's copy is the only one that no kernel overlaps.  Granules are multiples of `unit` rows (32 = whole CTA tiles,
+    // or the caller's band height).
+    const long long unit = band_rows > 0 ? band_rows : 32;
+    auto round_up = [&](long long v) { return std::max(unit, ceil_div(v, unit) * unit); };
+    const long long cap_units = std::max(unit, cap_rows / unit * unit);
+    s.round_off.clear();
+    if (per > 0) {
+        long long last = 0;
+        if (want_rounds >= 2) {
+            last = round_up(per / (4 * want_rounds));
+            if (last >= per) last = 0;
+        }
+        const long long body = per - last;
+        const long long granule = std::min(cap_units, round_up(ceil_div(body, std::max<long long>(1, want_rounds - (last ? 1 : 0)))));
+        for (long long a0 = 0; a0 < body; a0 += granule) s.round_off.push_back(a0);
+        if (last) s.round_off.push_back(body);
+        s.round_off.push_back(per);
     }
-    sub = std::min(sub, std::max<long long>(per, 1));
-    s.sub_rows = std::max<long long>(sub, 1);
+    s.rounds = s.round_off.empty() ? 0 : (long long)s.round_off.size() - 1;
+    s.sub_rows = 1;
+    for (long long k = 0; k < s.rounds; ++k) s.sub_rows = std::max(s.sub_rows, s.round_off[k + 1] - s.round_off[k]);
     s.slice_rows = band_rows > 0 ? std::min<long long>(band_rows, s.sub_rows) : s.sub_rows;
     s.slice_off = 0;
-    s.rounds = per > 0 ? ceil_div(per, s.sub_rows) : 0;
 
     const size_t band_doubles = (size_t)s.sub_rows * (size_t)cols1 * (size_t)n_exps;
     for (auto &d : ctx->dev) {

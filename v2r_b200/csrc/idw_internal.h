@@ -60,6 +60,7 @@ void fill_params(KParams &kp, const double *d_x, const double *d_y, const double
                  long long row0, long long nrows);
 int launch_poison(cudaStream_t stream, const double *d_x, const double *d_y, long long n, const v2r_idw_grid &g, long long row0,
                   long long nrows, double *d_out, int ne, unsigned *flag);
+double estimate_pair_rate(const double *exps, int n_exps, int precision);
 long long launch_count();
 void count_launch();
 int launch_patch_exact(cudaStream_t stream, const double *d_z, const long long *d_kr, const long long *d_kc, long long n,

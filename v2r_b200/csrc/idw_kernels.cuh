@@ -75,7 +75,7 @@ struct KParams {
     int segs;                 // point segments (function of n only)
     int seg_tiles;            // point tiles per segment
     double *scratch;          // tail partials: [tile - n_main][segment][accumulator][thread]
-    unsigned *counters;       // tail tiles: segments delivered so far (zero at launch, zero again at exit)
+    unsigned *counters;       // tail tiles: [0, R) segments delivered so far, [R, 2R) length of the prefix run (zero at launch)
     const GenTables *tables;  // MODE_GEN: table image in global memory (built once per device)
     double inv_x_step, inv_y_step;  // tile guard of the paired kernels (approximate reciprocals are enough)
 };
@@ -190,10 +190,12 @@ __device__ __forceinline__ unsigned run_piece(const KParams &p, Body &body, unsi
             body.points(p, sm[st][0], sm[st][1], sm[st][2], cnt, ctrl, it);
             __syncthreads();
         }
-        // end of segment `seg`: fold the segment sums into the running total (whole tiles: shared-memory stash,
-        // the last segment stays in registers) or hand them over (tail tiles: global scratch)
-        if (whole) {
-            if (seg + 1 < K) {
+        // end of segment `seg`: fold the segment sums into the running total -- whole tiles and the PREFIX run of a tail
+        // tile (s0 == 0: its sums are a prefix of the defined order, so they may be folded on the spot) use the
+        // shared-memory stash, the last segment of the run stays in registers -- or hand them over one by one (the
+        // other runs of a tail tile: global scratch)
+        if (whole || s0 == 0) {
+            if (seg + 1 < s1) {
                 if (seg == 0) {
 #pragma unroll
                     for (int i = 0; i < NACC; ++i) stash[i * THREADS + tid] = body.acc[i];
@@ -212,14 +214,23 @@ __device__ __forceinline__ unsigned run_piece(const KParams &p, Body &body, unsi
             for (int i = 0; i < NACC; ++i) body.acc[i] = 0.0;
         }
     }
-    if (whole) {
-        if (K > 1) {
+    if (whole || s0 == 0) {
+        if (s1 - s0 > 1) {
 #pragma unroll
             for (int i = 0; i < NACC; ++i) body.acc[i] = stash[i * THREADS + tid] + body.acc[i];
         }
+    }
+    if (whole) {
         body.store(p);
     } else {
         const long long slot = tile - (int)p.n_main;
+        const long long tail_tiles = p.n_tiles - p.n_main;
+        if (s0 == 0) {  // the prefix total S_0 + ... + S_{s1-1} goes into the scratch slot of its last segment
+            double *dst = p.scratch + ((slot * K + (s1 - 1)) * NACC) * THREADS + tid;
+#pragma unroll
+            for (int i = 0; i < NACC; ++i) __stcg(dst + (long long)i * THREADS, body.acc[i]);
+            if (tid == 0) p.counters[tail_tiles + slot] = (unsigned)s1;  // prefix length, read by the finisher
+        }
         __threadfence();
         __syncthreads();
         if (tid == 0) {
@@ -227,18 +238,18 @@ __device__ __forceinline__ unsigned run_piece(const KParams &p, Body &body, unsi
             ctrl->finisher = (old + (unsigned)(s1 - s0) == (unsigned)K);
         }
         __syncthreads();
-        if (ctrl->finisher) {  // every segment of this tile is in scratch: add them in segment order
+        if (ctrl->finisher) {  // every segment of this tile is in scratch: prefix total, then the rest in segment order
             __threadfence();
-            const double *src = p.scratch + (slot * K * NACC) * THREADS + tid;
+            const int L = (int)__ldcg(&p.counters[tail_tiles + slot]);
+            const double *src = p.scratch + ((slot * K + (L - 1)) * NACC) * THREADS + tid;
 #pragma unroll
             for (int i = 0; i < NACC; ++i) body.acc[i] = __ldcg(src + (long long)i * THREADS);
-            for (int s = 1; s < K; ++s) {  // segment order, NACC independent loads in flight per step
+            for (int s = L; s < K; ++s) {  // NACC independent loads in flight per step
                 src += (long long)NACC * THREADS;
 #pragma unroll
                 for (int i = 0; i < NACC; ++i) body.acc[i] += __ldcg(src + (long long)i * THREADS);
             }
             body.store(p);
-            if (tid == 0) p.counters[slot] = 0;  // leave the counters clean for the next launch
         }
         __syncthreads();
     }

@@ -215,6 +215,21 @@ static double model_ops(const Pass &ps, const Variant &v) {
     return ops;
 }
 
+// Rough throughput of one GPU on a sweep (cell-point pairs per second), from the instruction model: used by the
+// contexts to decide into how many rounds a device's band is cut (idw_api.cu).  Measured: 2.6e12 at 6 slots (p = 2),
+// 0.45e12 at 36 (c3 sweep), 0.75e12 at 17.5 (general), 5.6e12 for the packed FP32 kernel.
+double estimate_pair_rate(const double *exps, int n_exps, int precision) {
+    std::vector<Pass> passes;
+    if (plan_sweep(exps, n_exps, passes) != V2R_IDW_OK) return 1e12;
+    double slots = 0;
+    for (const Pass &ps : passes) {
+        const Variant *v = pick_variant(ps);
+        slots += v ? model_ops(ps, *v) + (ps.mode == MODE_GEN ? 4.0 * ps.count : 0.0) : 8.0;
+    }
+    const double fp64 = 2.6e12 * 6.0 / std::max(slots, 1.0);
+    return precision == V2R_IDW_FP32 ? 2.0 * fp64 : fp64;
+}
+
 static std::atomic<long long> g_launches{0};
 long long launch_count() { return g_launches.load(); }
 void count_launch() { g_launches++; }
@@ -298,11 +313,12 @@ void plan_grid(KParams &kp, int tile_r, int tile_c, int slots) {
     }
 }
 
-// Stream-ordered scratch for the tail tiles: partials, then the arrival counters (zeroed), then one flag word.
+// Stream-ordered scratch for the tail tiles: partials, then the arrival counters and prefix lengths (2 R words, zeroed),
+// then one flag word.
 int alloc_scratch(cudaStream_t stream, KParams &kp, int nacc, int threads, void **block, unsigned **flag) {
     const long long R = kp.n_tiles - kp.n_main;
     const size_t partial = (size_t)R * kp.segs * nacc * threads * sizeof(double);
-    const size_t words = (size_t)R + 4;
+    const size_t words = 2 * (size_t)R + 4;
     cudaError_t ce = cudaMallocAsync(block, partial + words * sizeof(unsigned), stream);
     if (ce != cudaSuccess) {
         cudaGetLastError();
@@ -310,7 +326,7 @@ int alloc_scratch(cudaStream_t stream, KParams &kp, int nacc, int threads, void 
     }
     kp.scratch = reinterpret_cast<double *>(*block);
     kp.counters = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(*block) + partial);
-    if (flag) *flag = kp.counters + R;
+    if (flag) *flag = kp.counters + 2 * R;
     ce = cudaMemsetAsync(kp.counters, 0, words * sizeof(unsigned), stream);
     if (ce != cudaSuccess) return set_error(V2R_IDW_ECUDA, "cudaMemsetAsync: %s", cudaGetErrorString(ce));
     return V2R_IDW_OK;
