@@ -35,6 +35,9 @@ def main(rep, out):
                 d[f"{h} [{units[i]}]"] = r[i]
         launches.append(d)
     json.dump(launches, open(out + "_metrics.json", "w"), indent=1)
+    if len(sys.argv) > 3 and sys.argv[3] == "--metrics-only":   # captures taken without the source counters
+        print("wrote", out + "_metrics.json")
+        return
 
     src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "sass"]))))
     hi = [i for i, r in enumerate(src) if r and r[0] == "Address"][0]

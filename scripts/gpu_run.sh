@@ -6,6 +6,7 @@
 #   classes   one bench line per exponent class / workload (diagnostic bands) + the default bench
 #   tail      short c4 bands with and without the tail split (V2R_IDW_TAIL=0)
 #   ncu       --set full capture per kernel class (summarised on the box)
+#   ncu-more  rsqrt / root4 single-exponent kernels (full set) and the c5 4-exponent kernel (sections without source counters)
 #   ncu-lite  metrics-only: FP64-pipe active vs elapsed + DRAM bytes on short bands and the default launch, launch list of the bench
 #   multi     (gpurun --gpus N) multi-GPU tests, c2 weak (direct and NCCL-gather copy-out) and the default bench under
 #             torchrun; `multi <tag> quick` runs the default bench only
@@ -59,6 +60,24 @@ ncu)
     prof fp64_c5_e4_band16 idw_fp64 --workload c5 --band-rows 16
     prof fp64_rsqrt_p1_band512 idw_fp64 --workload c2 --exps 1.0 --band-rows 512
     prof fp64_root4_p15_band512 idw_fp64 --workload c2 --exps 1.5 --band-rows 512
+    ls -la ${O}_*metrics.json ;;
+ncu-more)   # the captures the `ncu` suite did not reach: single-exponent rsqrt / root4 kernels (full set), and the c5
+            # 4-exponent kernel WITHOUT the source counters (the instrumented passes of that kernel take minutes each)
+    prof() {
+        local name=$1 rx=$2; shift 2
+        python bench.py --steps 1 --warmup 3 $Q "$@" > ${O}_plain_$name.log 2>&1 &&
+        ncu --set full --clock-control none --import-source on -k regex:$rx -s 3 -c 1 -f -o ${O}_$name python bench.py --steps 1 --warmup 3 $Q "$@" > ${O}_ncu_$name.log 2>&1
+        echo "$name rc=$?"
+        python profiles/summarize_ncu.py ${O}_$name.ncu-rep ${O}_$name > ${O}_summ_$name.log 2>&1 && rm -f ${O}_$name.ncu-rep
+    }
+    prof fp64_rsqrt_p1_band512 idw_fp64 --workload c2 --exps 1.0 --band-rows 512
+    prof fp64_root4_p15_band512 idw_fp64 --workload c2 --exps 1.5 --band-rows 512
+    name=fp64_c5_e4_band16
+    python bench.py --steps 1 --warmup 3 $Q --workload c5 --band-rows 16 > ${O}_plain_$name.log 2>&1 &&
+    timeout 600 ncu --section SpeedOfLight --section ComputeWorkloadAnalysis --section LaunchStats --section Occupancy --section MemoryWorkloadAnalysis --section WarpStateStats \
+        --clock-control none -k regex:idw_fp64 -s 3 -c 1 -f -o ${O}_$name python bench.py --steps 1 --warmup 3 $Q --workload c5 --band-rows 16 > ${O}_ncu_$name.log 2>&1
+    echo "$name rc=$?"
+    python profiles/summarize_ncu.py ${O}_$name.ncu-rep ${O}_$name --metrics-only > ${O}_summ_$name.log 2>&1 && rm -f ${O}_$name.ncu-rep
     ls -la ${O}_*metrics.json ;;
 ncu-lite)   # metrics-only passes: FP64 pipe active vs elapsed + DRAM bytes on short bands and the default launch, launch list
     M=sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed,gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum

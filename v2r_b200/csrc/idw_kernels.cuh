@@ -453,7 +453,8 @@ struct Fp64Body {
                 if constexpr (FOLD) e.log2_c = p.cexp[0] * e.log2_c;
                 t->lg[i] = e;
             }
-            for (int j = threadIdx.x; j < kExpTab; j += THREADS) t->ex[j] = p.tables->ex[j];
+            for (int j = threadIdx.x; j < kExpTab; j += THREADS)
+                t->ex[j] = (K0 == GEN_SINGLE) ? exp_entry_single(p.tables->ex[j], j) : p.tables->ex[j];
             gt = t;
         }
     }

@@ -86,6 +86,21 @@ inline void build_gen_tables(GenTables &t) {
     for (int j = 0; j < kExpTab; ++j) t.ex[j] = (double)exp2l((long double)j / kExpTab);
 }
 
+// (hi & 0x000fffff) | 0x3ff00000.  With both constants as immediates the compiler needs two LOP3; with the constants in
+// registers (hidden from constant propagation) it is ONE three-input LOP3 -- an integer instruction costs the loop as
+// much as half an FP64 instruction.
+__host__ __device__ __forceinline__ int mantissa_hi(int hi) {
+#ifdef __CUDA_ARCH__
+    int mask, one, r;
+    asm("mov.b32 %0, 0x000fffff;" : "=r"(mask));
+    asm("mov.b32 %0, 0x3ff00000;" : "=r"(one));
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(hi), "r"(mask), "r"(one));  // (a & b) | c
+    return r;
+#else
+    return (hi & 0x000fffff) | 0x3ff00000;
+#endif
+}
+
 // ---- log2 ------------------------------------------------------------------------------------------------
 // Core: no special handling.  a must be a positive normal double for the result to mean anything.
 // Returns  scale * log2(a)  where `scale` is 1 (plain table, lg = kLg) or 512 c (folded table: log2_c pre-multiplied,
@@ -94,7 +109,7 @@ __host__ __device__ __forceinline__ double log2_core(double a, const LogEntry *t
                                                      double kscale) {
     const int hi = hi_word(a);
     const LogEntry t = tab[(hi >> (20 - kLogBits)) & (kLogTab - 1)];
-    const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(a));  // [1, 2)
+    const double m = make_double(mantissa_hi(hi), lo_word(a));                 // [1, 2)
     const double r = fma(m, t.inv_c, -1.0);                                    // |r| <= 2^-11
     const double kd = make_double(0x43300000, (int)((unsigned)hi >> 20)) - kMagicExp;  // unbiased exponent, exact
     double q = fma(lg2, r, lg1);
@@ -116,12 +131,19 @@ __host__ __device__ __forceinline__ double tab_log2_safe(double a, const LogEntr
     return log2_core(a, tab, kLg[0], kLg[1], kLg[2], 1.0);
 }
 
+// Table value for the single-factor scaling: the high word of 2^(j/512) minus (j << 11), so that adding N * 2048
+// (N = 512 n + j) to it yields hi + (n << 20) with ONE integer multiply-add and no masking of j.
+__host__ __device__ __forceinline__ double exp_entry_single(double e, int j) {
+    return make_double(hi_word(e) - (j << (20 - kExpBits)), lo_word(e));
+}
+
 // ---- exp2 ------------------------------------------------------------------------------------------------
 // 2^(T/512).  Scaling of the result by 2^n:
 //   EXP_ANY     any finite T or NaN: |T/512| >= 2040 is clamped, 2^n in two factors so overflow saturates to +inf and
 //               underflow rounds through the subnormals to 0 by the multiplies themselves;
 //   EXP_BOUNDED the caller guarantees |T/512| < 2040 (or NaN): no clamp, two factors;
-//   EXP_SINGLE  the caller guarantees |T/512| <= 1021: n is added to the table value's exponent field (integer add).
+//   EXP_SINGLE  the caller guarantees |T/512| <= 1021: n is added to the table value's exponent field by one integer
+//               multiply-add; `tab` must hold exp_entry_single() values.
 enum ExpMode : int { EXP_ANY = 0, EXP_BOUNDED = 1, EXP_SINGLE = 2 };
 
 template <int XM>
@@ -142,8 +164,8 @@ __host__ __device__ __forceinline__ double tab_exp2(double T, const double *tab)
     const double p = fma(q, g, 1.0);          // 2^(g/512)
     const double e = tab[N & (kExpTab - 1)];  // 2^(j/512) in [1, 2)
     if constexpr (XM == EXP_SINGLE) {
-        // floor(N / 512) << 20, added to the exponent field of e
-        const double s = make_double(hi_word(e) + (int)(((unsigned)N << (20 - kExpBits)) & 0xfff00000u), lo_word(e));
+        // the table holds hi - (j << 11): hi' + N * 2048 = hi + (floor(N / 512) << 20)
+        const double s = make_double(hi_word(e) + N * (1 << (20 - kExpBits)), lo_word(e));
         return p * s;
     } else {
         const int n = N >> kExpBits;          // floor(N / 512), |n| <= 2040
