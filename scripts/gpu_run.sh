@@ -123,7 +123,7 @@ tune)   # tuning builds against the defaults (V2R_IDW_TUNE=<tag>, see the varian
         V2R_IDW_TUNE=$t python bench.py --steps 2 --warmup 3 $Q --workload c5 --band-rows 128 > ${O}_tune_c5_$t.json 2>> ${O}.err
     done
     for t in c4x6 ys4x6; do V2R_IDW_TUNE=$t $B --workload c2 > ${O}_tune_c2_$t.json 2>> ${O}.err; done
-    for t in none f4x4 f2x8 f2x16; do V2R_IDW_TUNE=$t $B --workload c2 --precision fp32 > ${O}_tune_fp32_$t.json 2>> ${O}.err; done
+    for t in none f2x8; do V2R_IDW_TUNE=$t $B --workload c2 --precision fp32 > ${O}_tune_fp32_$t.json 2>> ${O}.err; done
     tail -3 ${O}.err; summ ${O}_tune_*.json ;;
 stream)
     python scripts/stream_timing.py > ${O}_stream_timing.log 2>&1; tail -5 ${O}_stream_timing.log

@@ -25,16 +25,18 @@ struct FVariant {
 #define V2R_FPACKED(TAG, CR, CC, ISO, THREADS, MINB)                                                                  \
     FVariant { MODE_RCP, 1, true, ISO, CR, CC, THREADS, MINB, idw_fp32_packed_kernel<CR, CC, ISO, THREADS, MINB>,     \
                smem_bytes(Fp32PackedBodyFor<CR, CC, ISO, THREADS, MINB>::BODY_BYTES, 2 * (CR) * (CC), THREADS), TAG }
+// cell blocks sized so that 2 * E * CR * CC FP64 accumulators + as many FP32 partials fit the register budget without
+// spilling (two CTAs per SM up to 6 exponents, one beyond)
 #define V2R_FROW(MODE)                                                                          \
-    V2R_FVARIANT(MODE, 1, 4, 4, 2), V2R_FVARIANT(MODE, 2, 2, 4, 2),                             \
-        V2R_FVARIANT(MODE, 3, 2, 2, 2), V2R_FVARIANT(MODE, 4, 2, 2, 2),                         \
+    V2R_FVARIANT(MODE, 1, 2, 4, 2), V2R_FVARIANT(MODE, 2, 2, 2, 2),                             \
+        V2R_FVARIANT(MODE, 3, 2, 2, 2), V2R_FVARIANT(MODE, 4, 1, 2, 2),                         \
         V2R_FVARIANT(MODE, 5, 1, 2, 2), V2R_FVARIANT(MODE, 6, 1, 2, 2),                         \
-        V2R_FVARIANT(MODE, 7, 1, 2, 2), V2R_FVARIANT(MODE, 8, 1, 2, 2),                         \
-        V2R_FVARIANT(MODE, 9, 1, 2, 2), V2R_FVARIANT(MODE, 10, 1, 2, 2)
+        V2R_FVARIANT(MODE, 7, 1, 2, 1), V2R_FVARIANT(MODE, 8, 1, 2, 1),                         \
+        V2R_FVARIANT(MODE, 9, 1, 2, 1), V2R_FVARIANT(MODE, 10, 1, 2, 1)
 
 static const FVariant kFVariants[] = {
     // tuning builds of the packed p = 2 kernel (cell block, CTAs per SM)
-    V2R_FPACKED("f4x8", 4, 8, true, 256, 1), V2R_FPACKED("f2x8", 2, 8, true, 256, 1), V2R_FPACKED("f2x16", 2, 16, true, 256, 1),
+    V2R_FPACKED("f2x8", 2, 8, true, 256, 1),   // (4x8 and 2x16 were measured too, 5 383 / 5 082; they spill and were dropped)
     // p = 2: packed FP32 (FFMA2 / FADD2 / FMUL2), two points per MUFU.RCP, squared row distances staged in shared
     // memory; 4x4 cells measured 5 604 G evals/s on c2 against 5 383 (4x8), 5 379 (2x8) and 5 082 (2x16)
     V2R_FPACKED(nullptr, 4, 4, true, 256, 1), V2R_FPACKED(nullptr, 4, 4, false, 256, 1),
