@@ -223,6 +223,21 @@ def num_threads() -> int:
 
 
 # --------------------------------------------------------------------------- file formats
+def _float_or_zero(tok: str) -> float:
+    """p.X, _ = strconv.ParseFloat(tok, 64) (read_data.go:104-106): a token Go cannot parse leaves 0; an out-of-range
+    one leaves +-Inf (ErrRange is dropped with the other errors).  Python's float() accepts three spellings Go does
+    not -- underscores, "nan(...)" and a signed nan -- and Go accepts hex floats (with a p exponent) that float() does not."""
+    t = tok.lower()
+    if "_" in t or "(" in t or t in ("+nan", "-nan"):
+        return 0.0
+    try:
+        if t.lstrip("+-").startswith("0x"):
+            return float.fromhex(tok) if "p" in t else 0.0
+        return float(tok)
+    except (ValueError, OverflowError):
+        return 0.0
+
+
 def read_text_data(path: str):
     """tools/processing/read_data.go:17-111 grammar: `POINTS n` + n lines `x y w`; optional `STEP`
     + `sx sy`; `ESTIMATE` + `xmin xmax` + `ymin ymax` (returns at ESTIMATE).  Returns
@@ -237,10 +252,16 @@ def read_text_data(path: str):
     for line in it:
         head = line.split()[0]  # a blank line panics in the reference (:40); IndexError here
         if head == "POINTS":
-            n = int(line[len("POINTS "):].strip())
+            # addPoints (:93-111): Atoi and ParseFloat errors are dropped (0 points / 0.0), and `data = addPoints(sc)` (:42)
+            # REPLACES whatever an earlier POINTS section read
+            try:
+                n = int(line.removeprefix("POINTS ").strip())
+            except ValueError:
+                n = 0
+            xs, ys, ws = [], [], []
             for _ in range(n):
                 f3 = next(it).split()
-                xs.append(float(f3[0])); ys.append(float(f3[1])); ws.append(float(f3[2]))
+                xs.append(_float_or_zero(f3[0])); ys.append(_float_or_zero(f3[1])); ws.append(_float_or_zero(f3[2]))
         elif head == "STEP":
             f2 = next(it).split()
             xinfo.step, yinfo.step = float(f2[0]), float(f2[1])

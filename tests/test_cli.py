@@ -3,6 +3,7 @@ fill SoA buffers, native BigTIFF sink, TransferType.  CPU tests use --plan (no G
 features/idw/idw_test.go through the CLI and compare a gpkg sweep with the oracle."""
 import json
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -58,6 +59,33 @@ def test_translate_matches_python_sink(tmp_path):
     raster_io.WriteGDAL(z, gd, str(tmp_path / "a.tiff"), (0, 0), (16, 13), (16, 13), True)
     run("translate", str(tmp_path / "a.tiff"), str(tmp_path / "a.asc"), "Int16")
     assert open(tmp_path / "a.asc", "rb").read() == O.aaigrid_int16_bytes(z, -1.0, 0.0, 1.0)
+
+
+def test_translate_rejects_damaged_headers_instead_of_reading_past_them(tmp_path):
+    """the BigTIFF reader of the C++ sink only trusts offsets that lie inside the header block it has read"""
+    import struct
+    z = np.arange(12, dtype=np.float64).reshape(3, 4)
+    gd = raster_io.CreateGDalInfo(0.0, 0.0, 1.0, 1.0, 7, "EPSG:2284")
+    good = tmp_path / "good.tiff"
+    raster_io.WriteGDAL(z, gd, str(good), (0, 0), (3, 4), (3, 4), True)
+    blob = bytearray(good.read_bytes())
+    for name, patch in (("ifd_far", lambda b: b.__setitem__(slice(8, 16), struct.pack("<Q", 1 << 40))),
+                        ("ifd_count", lambda b: b.__setitem__(slice(16, 24), struct.pack("<Q", 1 << 50))),
+                        ("short", lambda b: b.__delitem__(slice(10, len(b))))):
+        bad = bytearray(blob)
+        patch(bad)
+        f = tmp_path / f"{name}.tiff"
+        f.write_bytes(bytes(bad))
+        p = run("translate", str(f), str(tmp_path / "o.asc"), "Int16", check=False)
+        assert p.returncode == 1 and "[FATAL]" in p.stderr, (name, p.returncode, p.stderr)
+    # the ModelTransformationTag pointing outside the header block
+    (n,) = struct.unpack_from("<Q", blob, 16)
+    for i in range(n):
+        if struct.unpack_from("<H", blob, 24 + 20 * i)[0] == 34264:
+            struct.pack_into("<Q", blob, 24 + 20 * i + 12, 1 << 33)
+    (tmp_path / "xf.tiff").write_bytes(bytes(blob))
+    p = run("translate", str(tmp_path / "xf.tiff"), str(tmp_path / "o.asc"), "Int16", check=False)
+    assert p.returncode == 1 and "ModelTransformationTag" in p.stderr
 
 
 @pytest.mark.gpu
@@ -121,6 +149,62 @@ def test_txt_reader_error_cases(tmp_path):
     ok = plan("POINTS 3\n1 2 3\r\n+4.5 5e0 x\n2 2 9\nSTEP\n0.5 0.25\nESTIMATE\n0 5\n0 5")   # CRLF, '+', exponent; 'x' -> 0 like the dropped error
     p = json.loads(ok.stdout)
     assert ok.returncode == 0 and (p["rows"], p["cols"], p["points_in"]) == (24, 12, 3)      # int((1+5)/0.25), int((1+5)/0.5)
+
+
+def test_txt_readers_keep_the_dropped_error_semantics_of_addPoints(tmp_path):
+    """addPoints (read_data.go:93-111) drops the errors of Atoi and ParseFloat: a count Go cannot parse reads 0 points, a
+    number Go cannot parse is 0, an out-of-range number is +-Inf; and `data = addPoints(sc)` (:42) makes a later POINTS
+    section REPLACE an earlier one.  The C++ reader, the Python reader and the oracle's reader must agree."""
+    from v2r_b200 import read_data
+    text = ("POINTS 2\n9 9 9\n8 8 8\n"                          # replaced by the next section
+            "POINTS 7\r\n"
+            "1 2 3\n"
+            "0x1p-2 .5 5.\n"                                      # hex float with exponent, bare fractions
+            "1_0 0x10 +nan\n"                                     # Go: syntax errors -> 0 0 0
+            "1e999 -1e999 2\n"                                    # ErrRange keeps +-Inf
+            "inf -Infinity 4\n"
+            "nan(1) 1e 7\n"                                       # syntax errors -> 0 0
+            "+4.25E+1 -0.0 1e-320\n"                              # denormal
+            "POINTS x\n"                                          # Atoi fails -> 0 points: the point set is now EMPTY ...
+            "POINTS 3\n5 6 7\n6 7 8 trailing fields are ignored\n7 8 9\n"   # ... and this section is what remains
+            "STEP\n2 4 ignored\nESTIMATE\n0 10 99\n0 20\n")
+    f = tmp_path / "odd.txt"
+    f.write_text(text)
+    p = json.loads(run("idw", "-f", str(f), "--plan", "-e", "--dump-points", "10").stdout)
+    assert p["raw"] == [[5.0, 6.0, 7.0], [6.0, 7.0, 8.0], [7.0, 8.0, 9.0]] and p["points_in"] == 3
+    assert (p["rows"], p["cols"]) == (5, 5)                      # int((1+20)/4), int((1+10)/2)
+    x, y, w, _, xi, yi = read_data.ReadTextData(str(f))
+    assert [x.tolist(), y.tolist(), w.tolist()] == [[5.0, 6.0, 7.0], [6.0, 7.0, 8.0], [7.0, 8.0, 9.0]]
+    assert (xi.min, xi.max, xi.step, yi.min, yi.max, yi.step) == (0.0, 10.0, 2.0, 0.0, 20.0, 4.0)
+    ox, oy, ow, oxi, oyi = O.read_text_data(str(f))
+    assert np.array_equal(ox, x) and np.array_equal(ow, w) and (oxi.max, oyi.step) == (10.0, 4.0)
+    # the middle section on its own: every spelling, value by value (NaN-aware), C++ vs Python vs the oracle
+    f2 = tmp_path / "odd2.txt"
+    f2.write_text(text.split("POINTS x\n")[0].split("8 8 8\n")[1] + "ESTIMATE\n0 10\n0 20\n")
+    want = [[1.0, 2.0, 3.0], [0.25, 0.5, 5.0], [0.0, 0.0, 0.0], [np.inf, -np.inf, 2.0], [np.inf, -np.inf, 4.0], [0.0, 0.0, 7.0],
+            [42.5, -0.0, 1e-320]]
+    raw = run("idw", "-f", str(f2), "--plan", "-e", "--dump-points", "10").stdout
+    raw = re.sub(r"(?<![\d.e])-0(?=[,\]])", "-0.0", raw)       # printf prints -0.0 as "-0", which json reads as the integer 0
+    got = json.loads(raw.replace("-inf", "-Infinity").replace(" inf", " Infinity").replace("[inf", "[Infinity"))["raw"]
+    x, y, w = read_data.ReadTextData(str(f2))[:3]
+    ox, oy, ow = O.read_text_data(str(f2))[:3]
+    for k, (a, b, c) in enumerate(((x, y, w), (ox, oy, ow), tuple(np.array([r[i] for r in got]) for i in range(3)))):
+        cols = np.array([a, b, c]).T
+        assert np.array_equal(cols, np.array(want)), k
+        assert np.array_equal(np.signbit(cols), np.signbit(np.array(want))), k
+
+
+def test_gpkg_bbox_follows_go_min_max_with_nan_coordinates(tmp_path):
+    """ReadGeoPackage folds math.Min / math.Max over the points (read_data.go:158-162): a NaN coordinate makes the bound NaN
+    (std::fmin / np.nanmin would skip it); the grid then has no valid size (int(NaN)) and the run stops before any solve."""
+    from v2r_b200 import read_data
+    x, y, w = np.array([1.0, np.nan, 5.0]), np.array([2.0, 3.0, 4.0]), np.array([1.0, 2.0, 3.0])
+    f = str(tmp_path / "nan.gpkg")
+    workloads.write_gpkg(f, x, y, w)
+    _, _, _, _, xi, yi = read_data.ReadGeoPackage(f, "wsels", "elevation", 1.0, 1.0)
+    assert np.isnan(xi.min) and np.isnan(xi.max) and (yi.min, yi.max) == (2.0, 4.0)
+    p = run("idw", "-g", "-f", f, "--layer", "wsels", "--field", "elevation", "--sx", "1", "--sy", "1", "--plan", "-e", check=False)
+    assert '"cols": -9223372036854775808' in p.stdout and '"rows": 3' in p.stdout       # Go: int(NaN) on amd64
 
 
 def test_cpp_readers_parse_bit_exactly_and_dedupe_like_the_oracle(tmp_path):

@@ -44,18 +44,76 @@ inline bool next_tok(const char *&p, const char *e, Tok &t) {
     t.e = p;
     return true;
 }
-// strconv.ParseFloat: ok == false on a syntax error (the reference then uses 0 for points, fails for STEP/ESTIMATE)
+// Grammar of strconv.ParseFloat (Go 1.18, base prefix only for hex): decimal floats, hex floats WITH a p exponent,
+// [+-]inf / infinity and an unsigned nan in any case.  No underscores, no "nan(...)", no hex without exponent.
+inline bool go_float_syntax(const char *b, const char *e) {
+    auto ieq = [](const char *p, const char *q, const char *w) {
+        for (; *w; ++p, ++w)
+            if (p >= q || (*p | 0x20) != *w) return false;
+        return p == q;
+    };
+    if (ieq(b, e, "nan")) return true;
+    if (b < e && (*b == '+' || *b == '-')) ++b;
+    if (ieq(b, e, "inf") || ieq(b, e, "infinity")) return true;
+    bool hex = false;
+    if (e - b >= 2 && b[0] == '0' && (b[1] | 0x20) == 'x') { hex = true; b += 2; }
+    auto digit = [&](char c) { return (c >= '0' && c <= '9') || (hex && (c | 0x20) >= 'a' && (c | 0x20) <= 'f'); };
+    int nd = 0;
+    while (b < e && digit(*b)) { ++b; ++nd; }
+    if (b < e && *b == '.') { ++b; while (b < e && digit(*b)) { ++b; ++nd; } }
+    if (nd == 0) return false;
+    if (b == e) return !hex;
+    if ((*b | 0x20) != (hex ? 'p' : 'e')) return false;
+    ++b;
+    if (b < e && (*b == '+' || *b == '-')) ++b;
+    if (b == e) return false;
+    for (; b < e; ++b)
+        if (*b < '0' || *b > '9') return false;
+    return true;
+}
+// strconv.ParseFloat: ok == false on a syntax error (the reference then uses 0 for points, fails for STEP/ESTIMATE);
+// an out-of-range value is +-Inf (Go returns it with ErrRange, which addPoints drops: the value is used)
 inline double parse_float(Tok t, bool &ok) {
+    ok = go_float_syntax(t.b, t.e);
+    if (!ok) return 0.0;
     const char *b = t.b;
-    if (b < t.e && *b == '+') ++b;
+    if (*b == '+') ++b;
     double v = 0;
     auto r = std::from_chars(b, t.e, v);
-    if (r.ec == std::errc() && r.ptr == t.e) { ok = true; return v; }
-    std::string s(t.b, t.e);  // rare spellings (hex floats, "Infinity", out-of-range): let strtod decide
-    char *end = nullptr;
-    v = strtod(s.c_str(), &end);
-    ok = end && *end == 0 && end != s.c_str();
-    return ok ? v : 0.0;
+    if (r.ec == std::errc() && r.ptr == t.e) return v;
+    std::string s(t.b, t.e);  // hex floats and out-of-range values: strtod
+    return strtod(s.c_str(), nullptr);
+}
+// strconv.Atoi(strings.TrimSpace(s)) with the error dropped (read_data.go:95): an optional sign and decimal digits,
+// nothing else; anything that is not an integer gives 0 points
+inline long long go_atoi_or_zero(const char *b, const char *e) {
+    auto go_space = [](char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; };
+    while (b < e && go_space(*b)) ++b;
+    while (e > b && go_space(e[-1])) --e;
+    const char *d = b;
+    if (d < e && (*d == '+' || *d == '-')) ++d;
+    if (d >= e) return 0;
+    for (const char *q = d; q < e; ++q)
+        if (*q < '0' || *q > '9') return 0;
+    long long v = 0;
+    auto r = std::from_chars(d, e, v);
+    if (r.ec != std::errc()) return *b == '-' ? 0 : (long long)0x7fffffffffffffffLL;  // ErrRange: Atoi hands back the clamped value
+    return *b == '-' ? -v : v;
+}
+// math.Min / math.Max of Go: NaN wins over every finite value, -Inf (+Inf) wins over NaN
+inline double go_min(double a, double b) {
+    if (std::isinf(a) && a < 0) return a;
+    if (std::isinf(b) && b < 0) return b;
+    if (std::isnan(a) || std::isnan(b)) return std::nan("");
+    if (a == 0 && b == 0) return std::signbit(a) ? a : b;
+    return a < b ? a : b;
+}
+inline double go_max(double a, double b) {
+    if (std::isinf(a) && a > 0) return a;
+    if (std::isinf(b) && b > 0) return b;
+    if (std::isnan(a) || std::isnan(b)) return std::nan("");
+    if (a == 0 && b == 0) return std::signbit(a) ? b : a;
+    return a > b ? a : b;
 }
 inline double parse_strict(Tok t, const std::string &file) {
     bool ok;
@@ -71,9 +129,11 @@ ReadResult ReadTextData(const std::string &filepath, int epsg) {
         std::ifstream in(filepath, std::ios::binary);
         if (!in) throw Error("open " + filepath + ": no such file or directory");
         in.seekg(0, std::ios::end);
-        buf.resize((size_t)in.tellg());
+        const std::streamoff len = in.tellg();
+        if (len < 0) throw Error("read " + filepath + ": is not a regular file");
+        buf.resize((size_t)len);
         in.seekg(0);
-        in.read(&buf[0], (std::streamsize)buf.size());
+        if (len > 0) in.read(&buf[0], (std::streamsize)buf.size());
     }
     ReadResult r;
     r.points = tools::PointSet(1024);
@@ -96,8 +156,9 @@ ReadResult ReadTextData(const std::string &filepath, int epsg) {
         if (hl == 6 && !memcmp(head.b, "POINTS", 6)) {
             // strconv.Atoi(strings.TrimSpace(strings.TrimPrefix(line, "POINTS "))), error dropped -> 0
             const char *c = (l.e - l.b >= 7 && !memcmp(l.b, "POINTS ", 7)) ? l.b + 7 : l.b;
-            long n = strtol(std::string(c, l.e).c_str(), nullptr, 10);
-            for (long i = 0; i < n; ++i) {
+            const long long n = go_atoi_or_zero(c, l.e);
+            r.points = tools::PointSet(1024);  // `data = addPoints(sc)` (read_data.go:42): a later POINTS section replaces an earlier one
+            for (long long i = 0; i < n; ++i) {
                 Line pl;
                 if (!next_line(pl)) pl.b = pl.e = end;
                 const char *s = pl.b;
@@ -250,8 +311,8 @@ ReadResult ReadGeoPackage(const std::string &filename, const std::string &layer,
         if (rd_u32(off + 1) % 1000 != 1) throw Error("POINT geometries expected");
         double x = rd_f64(off + 5), y = rd_f64(off + 13);
         r.points.push_back(x, y, sqlite().column_double(s.st, 1));
-        r.xInfo.Min = std::fmin(r.xInfo.Min, x); r.xInfo.Max = std::fmax(r.xInfo.Max, x);
-        r.yInfo.Min = std::fmin(r.yInfo.Min, y); r.yInfo.Max = std::fmax(r.yInfo.Max, y);
+        r.xInfo.Min = go_min(r.xInfo.Min, x); r.xInfo.Max = go_max(r.xInfo.Max, x);  // math.Min / math.Max (read_data.go:158-162)
+        r.yInfo.Min = go_min(r.yInfo.Min, y); r.yInfo.Max = go_max(r.yInfo.Max, y);
     }
     return r;
 }
@@ -336,7 +397,11 @@ TiffLayout tiff_layout(const std::string &path) {
     if (f.gcount() < 16 || head[0] != 'I' || head[1] != 'I' || (uint8_t)head[2] != 43) throw Error(path + ": not a little-endian BigTIFF");
     auto u64 = [&](size_t o) { uint64_t v; memcpy(&v, &head[o], 8); return v; };
     auto u16 = [&](size_t o) { uint16_t v; memcpy(&v, &head[o], 2); return v; };
-    uint64_t ifd = u64(8), n = u64(ifd);
+    const uint64_t have = (uint64_t)f.gcount();
+    const uint64_t ifd = u64(8);
+    if (ifd > have || have - ifd < 8) throw Error(path + ": IFD outside the header block");
+    const uint64_t n = u64(ifd);
+    if (n > (have - ifd - 8) / 20) throw Error(path + ": IFD outside the header block");
     TiffLayout L;
     for (uint64_t i = 0; i < n; ++i) {
         size_t e = ifd + 8 + 20 * i;
@@ -345,8 +410,13 @@ TiffLayout tiff_layout(const std::string &path) {
         if (tag == 256) L.cols = (long long)val;
         if (tag == 257) L.rows = (long long)val;
         if (tag == 273) L.data_off = (long long)val;
-        if (tag == 34264) { memcpy(L.xf, &head[val], 128); L.has_xf = true; }
+        if (tag == 34264) {
+            if (val > have || have - val < 128 || u64(e + 4) != 16) throw Error(path + ": ModelTransformationTag outside the header block");
+            memcpy(L.xf, &head[val], 128);
+            L.has_xf = true;
+        }
     }
+    if (L.rows < 0 || L.cols < 0 || L.data_off < 0) throw Error(path + ": bad raster dimensions");
     return L;
 }
 
