@@ -586,8 +586,8 @@ __global__ void __launch_bounds__(256) peak_kernel(double *out, int iters) {
         if (t == 12345.678f) out[0] = t;
     } else if constexpr (WHICH == 4) {  // DFMA with three distinct register-pair sources (what the IDW kernels issue)
         double a[8], b[8], c[8];
-#pragma unroll
         const double rnd = 1e-12 * (double)((clock64() + threadIdx.x) & 1023);  // unknown at compile time: operands must live in registers
+#pragma unroll
         for (int j = 0; j < 8; ++j) { a[j] = s + j; b[j] = 0.999999 + rnd * (j + 1); c[j] = 1.000001 - rnd * (2 * j + 1); }
         for (int i = 0; i < iters; ++i) {
 #pragma unroll
@@ -601,8 +601,8 @@ __global__ void __launch_bounds__(256) peak_kernel(double *out, int iters) {
         if (t == 12345.678) out[0] = t;
     } else if constexpr (WHICH == 5) {  // DADD, two register sources
         double a[8], b[8];
-#pragma unroll
         const double rnd = 1e-12 * (double)((clock64() + threadIdx.x) & 1023);
+#pragma unroll
         for (int j = 0; j < 8; ++j) { a[j] = s + j; b[j] = rnd * (j + 1); }
         for (int i = 0; i < iters; ++i)
 #pragma unroll
