@@ -516,6 +516,8 @@ def parity_block(args, V, ctx, ps, xi, yi, grid, exps_c, prec, world, local, jr0
            "bit_equal_1gpu": bit_equal, "bit_equal_against": how, "exact_hits": int(inb.sum()), "exact_hits_bit_equal": hits_ok,
            "oracle": "oracle/libidw_oracle.so solve_cells (CPU restatement of calculateIDW): float64 terms summed in long double "
                      "(max_scaled_err) and in input order; scale = the same solve on |w|",
+           "pinning": "the reference's own goldens pin the oracle to +-0.5 (Int16 AAIGrid, tests/test_oracle_golden.py); the 1e-12 bar "
+                      "rests on the restatement of tools/utils.go + Go 1.18 math.Pow, cross-checked against long-double sums",
            "seconds": time.perf_counter() - t0, "pass": passed}
     if prec != _lib.FP64:
         par["max_rel_err"] = worst     # the observed accuracy of the FP32 path (north_star: ~1e-5)
