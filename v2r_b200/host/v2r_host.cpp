@@ -131,6 +131,16 @@ static std::string fmt_g(double v) {
     snprintf(b, sizeof b, "%g", v);
     return b;
 }
+// Go's %v of a float64 (features/idw/idw.go:63 "pow%v"): the shortest decimal that reads back as the same double,
+// in %g style -- 0.30000000000000004 stays 0.30000000000000004, 2 prints as 2
+static std::string fmt_v(double v) {
+    char b[64];
+    for (int prec = 1; prec <= 17; ++prec) {
+        snprintf(b, sizeof b, "%.*g", prec, v);
+        if (strtod(b, nullptr) == v || v != v) break;
+    }
+    return b;
+}
 
 // one streaming session: at most kMaxSweep exponents (include/v2r_idw.h)
 static void SweepSession(v2r_idw_ctx *ctx, const tools::PointSet &data, const std::string *outfiles, const tools::Info &xInfo,
@@ -156,7 +166,7 @@ void SweepSolve(const tools::PointSet &data, const std::vector<std::string> &out
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     if (channel)
         for (double p : pows)
-            channel("pow" + fmt_g(p) + " [" + std::to_string(rows) + "X" + std::to_string(cols) + "] completed in " + fmt_g(secs) + "s");
+            channel("pow" + fmt_v(p) + " [" + std::to_string(rows) + "X" + std::to_string(cols) + "] completed in " + fmt_g(secs) + "s");
 }
 
 static void SweepSession(v2r_idw_ctx *ctx, const tools::PointSet &data, const std::string *outfiles, const tools::Info &xInfo,

@@ -226,6 +226,15 @@ def _check_outfile(outfile: str):
         raise ValueError("excel output is outside the GPU path (dead from the CLI: cmd/idw.go:155 always writes .tiff)")
 
 
+def _go_v(v: float) -> str:
+    """Go's %v of a float64 ("pow%v", features/idw/idw.go:63): shortest round-trip digits in %g style."""
+    for prec in range(1, 18):
+        s = f"{v:.{prec}g}"
+        if float(s) == v or v != v:
+            break
+    return s
+
+
 def _send(channel, msg):
     if channel is None:
         return
@@ -243,7 +252,7 @@ def FullSolve(data: PointSet, outfile: str, xInfo: Info, yInfo: Info, proj: str,
     z = _ctx(ctx).solve(data, grid, [pow], precision)[0]
     gd = raster_io.GDalInfo(xInfo.min, yInfo.min, xInfo.step, yInfo.step, 7, proj)
     raster_io.WriteGDAL(z, gd, outfile, (0, 0), (rows, cols), (rows, cols), True)
-    _send(channel, f"pow{pow:g} [{rows}X{cols}] completed in {time.time() - start:.6f}s")
+    _send(channel, f"pow{_go_v(pow)} [{rows}X{cols}] completed in {time.time() - start:.6f}s")
     return z
 
 
@@ -271,5 +280,5 @@ def ChunkSolve(data: PointSet, outfile: str, xInfo: Info, yInfo: Info, chunkR: i
             raster_io.WriteGDAL(chunk, gd, outfile, (r0, c0), (rows, cols), chunk.shape, first)
             first = False
         full[r0:r0 + band.shape[1]] = band[0]
-    _send(channel, f"pow{pow:g} [{rows}X{cols}] completed in {time.time() - start:.6f}s")
+    _send(channel, f"pow{_go_v(pow)} [{rows}X{cols}] completed in {time.time() - start:.6f}s")
     return full
