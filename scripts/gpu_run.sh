@@ -11,6 +11,7 @@
 #   multi     (gpurun --gpus N) multi-GPU tests, c2 weak (direct and NCCL-gather copy-out) and the default bench under
 #             torchrun; `multi <tag> quick` runs the default bench only
 #   tune      tuning builds (cell blocks, staged dy^2) against the default kernels
+#   quick     a 90-second sanity pass for host-side changes: smoke(), the CLI tests, the small parity tests, one c2 bench line
 #   stream    streaming API against one whole-grid solve (scripts/stream_timing.py) and the CLI on c2 / c5-shaped inputs
 suite=${1:-tests}
 tag=${2:-r2}
@@ -128,5 +129,12 @@ tune)   # tuning builds against the defaults (V2R_IDW_TUNE=<tag>, see the varian
 stream)
     python scripts/stream_timing.py > ${O}_stream_timing.log 2>&1; tail -5 ${O}_stream_timing.log
     python scripts/cli_c2.py > ${O}_cli_c2.log 2>&1; tail -5 ${O}_cli_c2.log ;;
+quick)
+    timeout 30 python -c "import __graft_entry__ as g; g.smoke()" > ${O}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a ${O}_smoke.log
+    timeout 60 python -m pytest tests/test_cli.py tests/test_gpu_parity.py -m gpu -x -q \
+        -k "cli or golden or c1_vs or edge or stream or gpkg or error or tile_boundaries" > ${O}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a ${O}_pytest.log
+    tail -3 ${O}_pytest.log
+    timeout 40 python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu-baseline > ${O}_c2.json 2> ${O}.err; echo "bench rc=$?"
+    summ ${O}_c2.json ;;
 *) echo "unknown suite $suite"; exit 2 ;;
 esac
