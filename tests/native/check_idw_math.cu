@@ -88,6 +88,39 @@ int main() {
     }
     bad += !(max1 < 4e-16) + !(max12 < 6e-16) + !(max14 < 8e-16);
     bad += !std::isnan(pow_m1(0.0)) + !std::isnan(pow_m12(0.0)) + !std::isnan(pow_m14(0.0));   // d = 0 off-key -> NaN cell
+    // p = 2 with a shared reciprocal: two pairs (the formula of Fp64Body::paired_points) and four pairs (rcp_shared4)
+    // against the four separate quotients in long double; error relative to sum |w_i| / d2_i (the parity scale).  The
+    // squared distances cover the whole guarded domain of the four-point form, (2^-240, 2^121), with independent
+    // magnitudes, equal magnitudes and the corners.
+    double max2n = 0, max2d = 0, max4n = 0, max4d = 0;
+    for (long i = 0; i < 1000000; i++) {
+        double v[4], w[4];
+        const double common = U(g) * 360 - 240;
+        for (int k = 0; k < 4; ++k) {
+            const double e2 = (i % 3 == 0) ? common + U(g) : U(g) * 361 - 240;   // similar magnitudes, or anything
+            v[k] = std::exp2(e2 < 120 ? e2 : 120.0) * (1 + U(g));
+            if (i % 7 == 0) v[k] = make_double(hi_word(v[k]), (int)0xffffffff);
+            w[k] = (U(g) * 2 - 1) * std::exp2(U(g) * 40 - 20);
+        }
+        if (i == 0) for (int k = 0; k < 4; ++k) v[k] = 0x1p-240;
+        if (i == 1) for (int k = 0; k < 4; ++k) v[k] = 0x1p+121;
+        if (i == 2) { v[0] = v[1] = 0x1p-240; v[2] = v[3] = 0x1p+121; }
+        long double td = 0, tn = 0, ts = 0;
+        for (int k = 0; k < 4; ++k) { td += 1.0L / v[k]; tn += (long double)w[k] / v[k]; ts += fabsl((long double)w[k]) / v[k]; }
+        double sn, sd, r;
+        rcp_shared4(v[0], v[1], v[2], v[3], w[0], w[1], w[2], w[3], sn, sd, r);
+        bad += !(std::isfinite(sn * r) && std::isfinite(sd * r) && sd * r > 0);
+        max4d = fmax(max4d, fabs((double)((sd * r - td) / td)));
+        max4n = fmax(max4n, fabs((double)((sn * r - tn) / ts)));
+        // two pairs: (a+b) / (ab), (w0 b + w1 a) / (ab)
+        const double r2 = pow_m1(v[0] * v[1]);
+        const long double td2 = 1.0L / v[0] + 1.0L / v[1], tn2 = (long double)w[0] / v[0] + (long double)w[1] / v[1];
+        const long double ts2 = fabsl((long double)w[0]) / v[0] + fabsl((long double)w[1]) / v[1];
+        max2d = fmax(max2d, fabs((double)(((v[0] + v[1]) * r2 - td2) / td2)));
+        max2n = fmax(max2n, fabs((double)((fma(w[0], v[1], w[1] * v[0]) * r2 - tn2) / ts2)));
+    }
+    bad += !(max2d < 8e-16) + !(max2n < 8e-16) + !(max4d < 1.2e-15) + !(max4n < 1.2e-15);
+    fprintf(stderr, "shared reciprocal: max rel err 2 pairs den %.2e num %.2e, 4 pairs den %.2e num %.2e\n", max2d, max2n, max4d, max4n);
     fprintf(stderr, "base powers: max rel err rcp %.2e rsqrt %.2e root4 %.2e\n", max1, max12, max14);
     printf("%.3e %.3e %.3e %.3e %d\n", maxl, maxe, maxh, maxf, bad);
     return 0;

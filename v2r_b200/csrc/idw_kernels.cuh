@@ -426,7 +426,7 @@ __host__ __device__ constexpr int ys_points(int mode, int E, int CR, int CC, int
     return 0;
 }
 
-template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS_, bool PAIRED, int YSP>
+template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS_, bool PAIRED, int YSP, bool QUAD = false>
 struct Fp64Body {
     static constexpr int THREADS = THREADS_;
     static constexpr int WARPS = THREADS / 32;
@@ -434,7 +434,8 @@ struct Fp64Body {
     static constexpr int NACC = 2 * E * CR * CC;  // acc[((e*CR + a)*CC + b)*2 + {0: num, 1: den}]
     static constexpr int TAB_BYTES = (MODE == MODE_GEN) ? (int)sizeof(GenTables) : 0;
     static constexpr int BODY_BYTES = TAB_BYTES + YSP * H * (int)sizeof(double);
-    static_assert(YSP == 0 || (YSP % 2 == 0 && THREADS % H == 0 && CR % 2 == 0), "staging layout");
+    static_assert(YSP == 0 || (YSP % 4 == 0 && THREADS % H == 0 && CR % 2 == 0), "staging layout");
+    static_assert(!QUAD || (PAIRED && YSP > 0), "four points per reciprocal: a flavour of the paired, staged body");
 
     double acc[NACC];
     double cx[CC], cy[CR];
@@ -556,6 +557,44 @@ struct Fp64Body {
         }
     }
 
+    // four points per reciprocal (p = 2, staged dy^2 only; rcp_shared4, idw_math.cuh); [i, end) holds a multiple of four
+    // points: the same 22 FP64 instructions per four pairs as two paired steps, half the MUFU.RCP64H and seed moves
+    __device__ __forceinline__ void quad_points(const double *sx, const double *sw, int i, int end, const double *yq) {
+#pragma unroll 1
+        for (; i < end; i += 4) {
+            const double2 x01 = *reinterpret_cast<const double2 *>(sx + i), x23 = *reinterpret_cast<const double2 *>(sx + i + 2);
+            const double2 w01 = *reinterpret_cast<const double2 *>(sw + i), w23 = *reinterpret_cast<const double2 *>(sw + i + 2);
+            double qx[4][CC];
+#pragma unroll
+            for (int b = 0; b < CC; ++b) {
+                const double d0 = __dsub_rn(x01.x, cx[b]), d1 = __dsub_rn(x01.y, cx[b]);
+                const double d2 = __dsub_rn(x23.x, cx[b]), d3 = __dsub_rn(x23.y, cx[b]);
+                qx[0][b] = __dmul_rn(d0, d0);
+                qx[1][b] = __dmul_rn(d1, d1);
+                qx[2][b] = __dmul_rn(d2, d2);
+                qx[3][b] = __dmul_rn(d3, d3);
+            }
+#pragma unroll
+            for (int a = 0; a < CR; a += 2) {
+                const double2 y0 = *reinterpret_cast<const double2 *>(yq + a), y1 = *reinterpret_cast<const double2 *>(yq + H + a);
+                const double2 y2 = *reinterpret_cast<const double2 *>(yq + 2 * H + a), y3 = *reinterpret_cast<const double2 *>(yq + 3 * H + a);
+#pragma unroll
+                for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+                    for (int b = 0; b < CC; ++b) {
+                        const double A = __dadd_rn(qx[0][b], aa ? y0.y : y0.x), B = __dadd_rn(qx[1][b], aa ? y1.y : y1.x);
+                        const double Cc = __dadd_rn(qx[2][b], aa ? y2.y : y2.x), D = __dadd_rn(qx[3][b], aa ? y3.y : y3.x);
+                        double SN, SD, r;
+                        rcp_shared4(A, B, Cc, D, w01.x, w01.y, w23.x, w23.y, SN, SD, r);
+                        double &num = acc[((a + aa) * CC + b) * 2], &den = acc[((a + aa) * CC + b) * 2 + 1];
+                        num = fma(SN, r, num);
+                        den = fma(SD, r, den);
+                    }
+            }
+            yq += 4 * H;
+        }
+    }
+
     __device__ __forceinline__ void points(const KParams &p, const double *sx, const double *sy, const double *sw, int cnt,
                                            Ctrl *ctrl, unsigned it) {
         bool paired_ok = false;
@@ -564,8 +603,11 @@ struct Fp64Body {
             const int slot = it & 1;
             bool unsafe = false;
             const TileBox box = tile_box<32 * CC, H>(p, (long long)tile_c * (32 * CC), p.row0 + (long long)tile_r * H);
+            // two points: a b normal for d2 in (2^-500, 2^499); four points: ab cd and the cross products (a+b) cd,
+            // (w0 b + w1 a) cd need d2 in (2^-240, 2^121) -- beyond 2^60 grid units a tile takes the one-reciprocal loop
+            constexpr double kTiny = QUAD ? 0x1p-120 : 0x1p-250, kFar = QUAD ? 0x1p+60 : 0x1p+249;
             for (int k = threadIdx.x; k < cnt; k += THREADS)
-                unsafe |= pairing_unsafe<32 * CC, H>(sx[k], sy[k], p, box, 0x1p-250, 0x1p+249);
+                unsafe |= pairing_unsafe<32 * CC, H>(sx[k], sy[k], p, box, kTiny, kFar);
             if (unsafe) ctrl->guard[slot] = 1;
             __syncthreads();
             paired_ok = !ctrl->guard[slot];
@@ -587,8 +629,13 @@ struct Fp64Body {
                 int i = h0;
                 if constexpr (PAIRED) {
                     if (paired_ok) {
-                        paired_points(sx, sy, sw, h0, h0 + (hn & ~1), yq);
-                        i = h0 + (hn & ~1);
+                        if constexpr (QUAD) {
+                            quad_points(sx, sw, h0, h0 + (hn & ~3), yq);
+                            i = h0 + (hn & ~3);
+                        } else {
+                            paired_points(sx, sy, sw, h0, h0 + (hn & ~1), yq);
+                            i = h0 + (hn & ~1);
+                        }
                     }
                 }
                 single_points(p, sx, sy, sw, i, h0 + hn, yq + (long long)(i - h0) * H);
@@ -624,9 +671,9 @@ struct Fp64Body {
     }
 };
 
-// OPT: bit 0 = paired reciprocal (p = 2), bit 1 = dy^2 staged in shared memory
+// OPT: bit 0 = paired reciprocal (p = 2), bit 1 = dy^2 staged in shared memory, bit 2 = four points per reciprocal
 template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS, int MINB, int OPT>
-using Fp64BodyFor = Fp64Body<MODE, E, CR, CC, K0, DK, THREADS, (OPT & 1) != 0, (OPT & 2) ? ys_points(MODE, E, CR, CC, THREADS, MINB) : 0>;
+using Fp64BodyFor = Fp64Body<MODE, E, CR, CC, K0, DK, THREADS, (OPT & 1) != 0, (OPT & 2) ? ys_points(MODE, E, CR, CC, THREADS, MINB) : 0, (OPT & 4) != 0>;
 
 template <int MODE, int E, int CR, int CC, int K0, int DK, int THREADS, int MINB, int OPT = 0>
 __global__ void __launch_bounds__(THREADS, MINB) idw_fp64_kernel(const __grid_constant__ KParams p) {

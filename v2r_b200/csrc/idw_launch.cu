@@ -139,6 +139,7 @@ static const Variant kVariants[] = {
     V2R_TUNE("g2x2", MODE_GEN, 1, 2, 2, GEN_SINGLE, 0, 256, 2), V2R_TUNE("g4x4", MODE_GEN, 1, 4, 4, GEN_SINGLE, 0, 256, 1),
     V2R_TUNE("g4x2", MODE_GEN, 1, 4, 2, GEN_SINGLE, 0, 256, 2),
     V2R_PAIRED("c4x6", 4, 6, 256, 1), V2R_PAIRED_YS("ys4x6", 4, 6, 256, 1),
+    V2R_KERNEL(MODE_RCP, 1, 4, 4, 1, 0, 256, 1, 7, true, "quad"),  // p = 2, FOUR points per reciprocal (half the MUFU + seed moves)
     V2R_PAIRED("nys", 4, 4, 256, 1),                // p = 2, paired, every lane computes its own dy^2 (round 1's loop)
     V2R_UNSTAGED("nys", MODE_RSQ, 1, 2, 4, 1, 0, 256, 2), V2R_UNSTAGED("nys", MODE_QRT, 1, 2, 4, 3, 0, 256, 2),
     V2R_UNSTAGED("nys", MODE_QRT, 9, 2, 2, 1, 1, 256, 1), V2R_UNSTAGED("nys", MODE_QRT, 4, 2, 2, 2, 1, 256, 2),

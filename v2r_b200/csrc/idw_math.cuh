@@ -206,6 +206,19 @@ __host__ __device__ __forceinline__ double pow_m1(double a) {
     double t = fma(e, e, e);
     return fma(r0, t, r0);
 }
+// FOUR pairs under one reciprocal (p = 2: h = 1/d2).  With a, b, c, d the four squared distances of a cell,
+//   1/a + 1/b + 1/c + 1/d         = ((a+b) cd + (c+d) ab) / (ab cd)                      = sd * r
+//   w0/a + w1/b + w2/c + w3/d     = ((w0 b + w1 a) cd + (w2 d + w3 c) ab) / (ab cd)      = sn * r ,   r = 1 / (ab cd)
+// 20 FP64 instructions + the two accumulations = 22 per four pairs (as many as two two-point steps) and ONE MUFU.RCP64H.
+// Needs ab cd and the cross products normal: every squared distance in (2^-240, 2^121) (the caller's tile guard).
+__host__ __device__ __forceinline__ void rcp_shared4(double a, double b, double c, double d, double w0, double w1, double w2,
+                                                     double w3, double &sn, double &sd, double &r) {
+    const double p1 = a * b, p2 = c * d;
+    r = pow_m1(p1 * p2);
+    const double n1 = fma(w0, b, w1 * a), n2 = fma(w2, d, w3 * c);
+    sn = fma(n1, p2, n2 * p1);
+    sd = fma(a + b, p2, (c + d) * p1);
+}
 // a^(-1/2): e = 1 - a y0^2 ; y = y0 (1 + e/2 + 3 e^2/8).  5 FP64 + 1 MUFU.
 __host__ __device__ __forceinline__ double pow_m12(double a) {
     double y0 = rsq_seed(a);
