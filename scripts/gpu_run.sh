@@ -12,6 +12,8 @@
 #             torchrun; `multi <tag> quick` runs the default bench only
 #   tune      tuning builds (cell blocks, staged dy^2) against the default kernels
 #   quick     a 90-second sanity pass for host-side changes: smoke(), the CLI tests, the small parity tests, one c2 bench line
+#   quad      the p = 2 tuning build with four points per reciprocal (V2R_IDW_TUNE=quad): small parity tests, then c2 and a
+#             32-row c4 band against the default build, parity block included
 #   stream    streaming API against one whole-grid solve (scripts/stream_timing.py) and the CLI on c2 / c5-shaped inputs
 suite=${1:-tests}
 tag=${2:-r2}
@@ -136,5 +138,13 @@ quick)
     tail -3 ${O}_pytest.log
     timeout 40 python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu-baseline > ${O}_c2.json 2> ${O}.err; echo "bench rc=$?"
     summ ${O}_c2.json ;;
+quad)
+    V2R_IDW_TUNE=quad timeout 30 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
+        -k "c1_vs or tile_boundaries or edge_semantics or paired_kernels or randomized or row_bands or golden" > ${O}_pytest.log 2>&1
+    echo "pytest(quad) rc=$?" | tee -a ${O}_pytest.log; tail -2 ${O}_pytest.log
+    timeout 12 python bench.py --workload c2 --steps 3 --warmup 3 $Q > ${O}_c2_default.json 2>> ${O}.err
+    V2R_IDW_TUNE=quad timeout 14 python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu-baseline --parity-cells 500 > ${O}_c2_quad.json 2>> ${O}.err
+    V2R_IDW_TUNE=quad timeout 16 python bench.py --slab 7168:32 --steps 3 --warmup 3 --no-cpu-baseline --parity-cells 150 > ${O}_c4rows32_quad.json 2>> ${O}.err
+    tail -3 ${O}.err; summ ${O}_c2_default.json ${O}_c2_quad.json ${O}_c4rows32_quad.json ;;
 *) echo "unknown suite $suite"; exit 2 ;;
 esac
