@@ -1,6 +1,7 @@
 """Accuracy of the device arithmetic in v2r_b200/csrc/idw_math.cuh -- the table-driven log2/exp2 of the `general`
 exponent class and the seed + one-cubic-step reciprocal / rsqrt / fourth-root of the other classes (with the MUFU
-seeds emulated at their documented 20-bit worst case) -- checked on the CPU: the header is __host__ __device__, so nvcc builds it into a host program that compares 2 M samples over
+seeds emulated at their documented 20-bit worst case), and the p = 2 shared-reciprocal forms (two pairs, and the four
+pairs of rcp_shared4 over their whole guarded domain of squared distances, 2^-240 .. 2^121) -- checked on the CPU: the header is __host__ __device__, so nvcc builds it into a host program that compares 2 M samples over
 60 decades with long-double libm, plus every special value the kernels rely on (d2 = 0 -> -inf -> h = +inf -> NaN
 cell; saturation to 0 / +inf; NaN passes through)."""
 import os
