@@ -81,13 +81,22 @@ def job_rows(args, grid_rows):
     return r0, max(0, min(nr, grid_rows - r0))
 
 
+def make_config(args, world, n, E, jr0, jnr, nrows, cols):
+    """`config` of the JSON line: the job -- identical in both arms (the reference arm times a bounded sample of this job;
+    what the sample was is said in cpu_baseline.sample)."""
+    return {"workload": _workload_name(args, world), "points_after_dedupe": int(n), "exponents": int(E),
+            "job_rows": [int(jr0), int(jr0 + jnr)], "rows_per_rank": int(nrows), "cols": int(cols),
+            "l2": "GPU arm: flushed between timed iterations (256 MiB memset); output band > L2",
+            "parallelism": f"row bands x{world}"}
+
+
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_sample(args, seconds):
+def cpu_sample(args, seconds, world=1):
     """Times the oracle (CPU restatement of the reference, `-c` concurrent mode) on a bounded sample of
     the workload: the first rows of the job against the full point set, all host threads."""
     from oracle import oracle as O
     from v2r_b200 import workloads
-    x, y, w, xi, yi, exps = workloads.make(args.workload)
+    x, y, w, xi, yi, exps = workloads.make(args.workload, scale_rows=world if args.scaling == "weak" else 1)   # as the GPU arm
     if args.exps:
         exps = np.array([float(v) for v in args.exps.split(",")])
     oi = lambda i: O.Info(i.min, i.max, i.step)  # noqa: E731
@@ -125,14 +134,18 @@ def cpu_sample(args, seconds):
     ncells = int(max(threads, min(jnr * cols, seconds / max(t_cell, 1e-9))))
     ncells = max(threads, ncells // threads * threads)
     return dict(run=lambda: run(ncells), run_serial=run_serial, evals=float(ncells) * n, E=E, threads=threads,
-                ncells=ncells, cols=cols, n=n, row0=jr0)
+                ncells=ncells, cols=cols, n=n, row0=jr0, job_nrows=jnr)
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    s = cpu_sample(args, args.cpu_seconds)
+    from v2r_b200.distributed import shard_rows
+    world = max(1, args.gpus)
+    s = cpu_sample(args, args.cpu_seconds, world)
+    band = shard_rows(s["job_nrows"], world, 0)[1]          # rank 0's share of the job in the GPU arm
+    nrows = band if args.band_rows <= 0 else min(args.band_rows, band)
     for _ in range(min(args.warmup, 1)):  # CPU code has no clocks to warm; one pass touches the pages
         s["run"]()
     t = 0.0
@@ -145,7 +158,7 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 0, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": _workload_name(args, 1), "sample": sample},
+        "config": make_config(args, world, s["n"], s["E"], s["row0"], s["job_nrows"], nrows, s["cols"]),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": s["threads"], "kind": "port", "sample": sample,
                          "serial": s["run_serial"]()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -368,7 +381,7 @@ def ours(args):
             }
         cpu = None
         if not args.no_cpu_baseline:
-            s = cpu_sample(args, args.cpu_seconds)
+            s = cpu_sample(args, args.cpu_seconds, world)
             tc = s["run"]()
             cpu = {"value": s["evals"] / tc / 1e9, "unit": UNIT, "cores": s["threads"], "kind": "port",
                    "sample": f"the first {s['ncells']} cells (row-major from row {s['row0']}) of the job x {s['n']} points x {s['E']} exponent(s) of {args.workload}, "
@@ -379,10 +392,7 @@ def ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64" if prec == _lib.FP64 else "f32(tile)/f64(accumulate)",
             "data": "synthetic",
-            "config": {"workload": _workload_name(args, world), "points_after_dedupe": n, "exponents": E,
-                       "job_rows": [jr0, jr0 + jnr], "rows_per_rank": nrows, "cols": int(grid.cols),
-                       "l2": "flushed between timed iterations (256 MiB memset); output band > L2",
-                       "parallelism": f"row bands x{world}"},
+            "config": make_config(args, world, n, E, jr0, jnr, nrows, grid.cols),
             "pair_evals_per_step": pair_evals_step, "raster_evals_per_s_G": value * E,
             "wall_s": t_wall, "clocks": clk, "e2e": e2e, "parity": parity, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,

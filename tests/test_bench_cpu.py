@@ -62,3 +62,23 @@ def test_reference_arm_prints_the_contract_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "points" in cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # `config` is the job, built by the same function as the GPU arm's (the sample is described in cpu_baseline.sample)
+    a = _args(workload="c2")
+    assert line["config"] == bench.make_config(a, 1, 99699, 1, 0, 4096, 4096, 4096)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2", "--gpus", "8", "--steps", "1",
+                        "--warmup", "0", "--cpu-seconds", "0.3"], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, RANK="0", WORLD_SIZE="8"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    cfg = json.loads(p.stdout.strip().splitlines()[-1])["config"]
+    assert cfg == bench.make_config(a, 8, 99699, 1, 0, 4096, 512, 4096) and cfg["parallelism"] == "row bands x8"
+
+
+def test_config_of_the_default_job():
+    """what the driver's run prints as `config` at N = 1 and N = 8 (both arms call make_config with these values)"""
+    a = _args()
+    c1 = bench.make_config(a, 1, 967142, 1, 7168, 2048, 2048, 16384)
+    c8 = bench.make_config(a, 8, 967142, 1, 7168, 2048, 256, 16384)
+    assert c1["workload"] == c8["workload"] and "slab rows [7168,9216)" in c1["workload"]
+    assert c1["job_rows"] == [7168, 9216] and (c1["rows_per_rank"], c8["rows_per_rank"]) == (2048, 256)
+    assert c1["points_after_dedupe"] == 967142 and c1["cols"] == 16384 and "flushed" in c1["l2"]
+    assert json.loads(json.dumps(c8)) == c8
