@@ -6,12 +6,18 @@
 // result with the CPU oracle at the parity bar -- GPU-free evidence that the scheme itself (not one lucky data set) meets
 // 1e-12, for every grouping, on clustered points and signed weights.  This is test code: it is not the kernel.
 //
-//   emulate_p2 <in.bin> <out.bin>
+// With a third argument the same scheme runs for any exponent p with one point per base power, through the class the
+// dispatcher would pick (plan_sweep, idw_launch.cu): rcp (p even), rsqrt (p integer), root4 (2p integer), general
+// (folded table log2 / exp2 for 0 < p <= 3.75, saturating forms otherwise; p == 0 gives h = 1).
+//
+//   emulate_p2 <in.bin> <out.bin> [p]
 //   in : int64 n, m, group; double x_min, x_step, y_min, y_step; double x[n], y[n], w[n]; int64 r[m], c[m]
 //   out: double z[m]
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <vector>
 
 #include "idw_math.cuh"
@@ -19,8 +25,47 @@ using namespace v2r;
 
 static const int kTilePoints = 512, kMaxSegs = 16, kChunk = 256;  // kTilePoints / kMaxSegs / ys_points() of the 4x4 p = 2 build
 
+static double ipow_rt(double b, int k) {   // the kernels' runtime ladder (idw_kernels.cuh)
+    double r = b;
+    bool have = (k & 1);
+    k >>= 1;
+    while (k) {
+        b *= b;
+        if (k & 1) { r = have ? r * b : b; have = true; }
+        k >>= 1;
+    }
+    return r;
+}
+
+// h(d2) = d2^(-p/2) the way the class of p computes it
+static std::function<double(double)> weight_of(double p) {
+    const bool half = p > 0 && std::floor(2 * p) == 2 * p && p <= 32;
+    if (half && std::floor(p / 2) == p / 2) { const int k = (int)(p / 2); return [k](double a) { return ipow_rt(pow_m1(a), k); }; }
+    if (half && std::floor(p) == p) { const int k = (int)p; return [k](double a) { return ipow_rt(pow_m12(a), k); }; }
+    if (half) { const int k = (int)(2 * p); return [k](double a) { return ipow_rt(pow_m14(a), k); }; }
+    static GenTables gt, ft;
+    static double exs[kExpTab];
+    build_gen_tables(gt);
+    const double cs = kExpScale * (-p / 2.0);
+    if (p > 0 && p <= 3.75) {   // GEN_SINGLE / GEN_SAFE: the multiplier folded into the log table and series (Fp64Body constructor)
+        ft = gt;
+        for (int i = 0; i < kLogTab; ++i) ft.lg[i].log2_c = cs * gt.lg[i].log2_c;
+        for (int j = 0; j < kExpTab; ++j) exs[j] = exp_entry_single(gt.ex[j], j);
+        const double l0 = cs * kLg[0], l1 = cs * kLg[1], l2 = cs * kLg[2];
+        const bool single = p <= 1.99;
+        return [=](double a) {
+            const double T = log2_core(a, ft.lg, l0, l1, l2, cs);
+            return single ? tab_exp2<EXP_SINGLE>(T, exs) : tab_exp2<EXP_BOUNDED>(T, ft.ex);
+        };
+    }
+    return [cs](double a) { return tab_exp2<EXP_ANY>(cs * tab_log2_any(a, gt.lg), gt.ex); };   // GEN_ANY
+}
+
 int main(int argc, char **argv) {
-    if (argc != 3) return 2;
+    if (argc != 3 && argc != 4) return 2;
+    const bool any_p = argc == 4;
+    std::function<double(double)> hfun = [](double a) { return pow_m1(a); };
+    if (any_p) hfun = weight_of(atof(argv[3]));
     FILE *f = fopen(argv[1], "rb");
     if (!f) return 2;
     int64_t n, m, group;
@@ -58,7 +103,8 @@ int main(int argc, char **argv) {
                         return dx2 + dy2;
                     };
                     int64_t i = h0;
-                    if (group == 4) {
+                    if (any_p) {
+                    } else if (group == 4) {
                         for (; i + 4 <= h0 + (hn & ~3LL); i += 4) {
                             double sn, sd, rr;
                             rcp_shared4(d2(i), d2(i + 1), d2(i + 2), d2(i + 3), w[base + i], w[base + i + 1], w[base + i + 2], w[base + i + 3],
@@ -76,7 +122,7 @@ int main(int argc, char **argv) {
                         }
                     }
                     for (; i < h0 + hn; ++i) {
-                        const double h = pow_m1(d2(i));
+                        const double h = hfun(d2(i));
                         num = fma(w[base + i], h, num);
                         den += h;
                     }

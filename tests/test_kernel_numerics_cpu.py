@@ -1,4 +1,4 @@
-"""GPU-free check of the numerical scheme of the p = 2 FP64 kernels: tests/native/emulate_p2.cu restates it on the host
+"""GPU-free check of the numerical scheme of the FP64 kernels (p = 2 in all its groupings, and every exponent class): tests/native/emulate_p2.cu restates it on the host
 (512-point tiles in <= 16 segments folded in segment order; 4 / 2 / 1 points per reciprocal from idw_math.cuh with the
 MUFU seeds emulated at their 20-bit worst case) and the result is held to the CPU oracle at the parity bar of the GPU
 tests -- on uniform and clustered points, signed weights, EPSG:2284 magnitudes and point counts around every tile /
@@ -29,7 +29,7 @@ def emulator(tmp_path_factory):
     return exe
 
 
-def emulate(exe, tmp, ps, xi, yi, rr, cc, group):
+def emulate(exe, tmp, ps, xi, yi, rr, cc, group, p=None):
     fin, fout = os.path.join(tmp, f"in{group}.bin"), os.path.join(tmp, f"out{group}.bin")
     with open(fin, "wb") as f:
         f.write(struct.pack("<qqq4d", len(ps), len(rr), group, xi.min, xi.step, yi.min, yi.step))
@@ -37,7 +37,7 @@ def emulate(exe, tmp, ps, xi, yi, rr, cc, group):
             f.write(np.ascontiguousarray(a, dtype="<f8").tobytes())
         for a in (rr, cc):
             f.write(np.ascontiguousarray(a, dtype="<i8").tobytes())
-    subprocess.check_call([exe, fin, fout])
+    subprocess.check_call([exe, fin, fout] + ([] if p is None else [repr(float(p))]))
     return np.fromfile(fout, dtype="<f8")
 
 
@@ -87,3 +87,23 @@ def test_scheme_at_tile_chunk_and_segment_boundaries(emulator, tmp_path, n):
     rng = np.random.default_rng(1000 + n)
     x, y = rng.uniform(-3, 103, n), rng.uniform(-3, 63, n)
     check(emulator, str(tmp_path), x, y, rng.normal(0, 50, n), O.Info(0.0, 99.0, 0.7), O.Info(0.0, 59.0, 0.7), 120, n, f"n={n}")
+
+
+@pytest.mark.parametrize("p", [1.0, 3.0, 4.0, 0.5, 1.5, 4.5, 1.7, 0.3, 0.30000000000000004, 1.99, 2.2, 3.75, 4.2, 0.0, -1.0])
+def test_scheme_in_every_exponent_class(emulator, tmp_path, p):
+    """rcp / rsqrt / root4 ladders and the three flavours of the general class (folded single-factor, folded two-factor,
+    saturating) from idw_math.cuh, one point per base power, against the oracle's Go Pow: signed weights, 20 k points."""
+    rng = np.random.default_rng(7)
+    n = 20_000
+    xi, yi = O.Info(0.0, 19_999.0, 50.0), O.Info(0.0, 9_999.0, 50.0)
+    ps = O.make_coord_space(rng.uniform(0, 20_000, n), rng.uniform(0, 10_000, n), rng.normal(0, 100, n), xi, yi)
+    rows, cols = O.get_dimensions(xi, yi)
+    rr, cc = rng.integers(0, rows, 300), rng.integers(0, cols, 300)
+    keys = set(zip(ps.key_r.tolist(), ps.key_c.tolist()))
+    keep = np.array([(int(a), int(b)) not in keys for a, b in zip(rr, cc)])
+    rr, cc = rr[keep], cc[keep]
+    ref = O.solve_cells(ps, xi, yi, p, rr, cc, mode=O.SUM_LONG_DOUBLE)
+    scale = O.solve_cells(O.PointSet(ps.x, ps.y, np.abs(ps.w), ps.key_r, ps.key_c), xi, yi, p, rr, cc, mode=O.SUM_LONG_DOUBLE)
+    z = emulate(emulator, str(tmp_path), ps, xi, yi, rr, cc, 1, p)
+    err = float(np.max(np.abs(z - ref) / np.maximum(np.abs(ref), scale)))
+    assert np.isfinite(z).all() and err <= REL, f"p={p}: {err:.3e}"
