@@ -132,3 +132,53 @@ def test_workloads_have_the_named_shapes(tmp_path):
     assert np.array_equal(x, x3) and np.array_equal(y, y3) and np.array_equal(w, w3) and xi3.max == x.max()
     x4, y4, w4, p4, _, _ = read_data.ReadGeoPackage(os.path.join(ROOT, "tests", "golden", "input.gpkg"), "wsels", "elevation", 1.0, 2.0)
     assert len(x4) == 14 and p4.startswith("PROJCS[")
+
+
+# ---- property tests: the C ABI's host helpers (C++, idw_api.cu) against the oracle's (C, idw_oracle.c) -----------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_f = st.one_of(st.floats(allow_nan=True, allow_infinity=True, width=64),
+               st.floats(min_value=-1e7, max_value=1e7, allow_nan=False),
+               st.sampled_from([0.0, -0.0, 1.0, 0.1, 100.0, 0.30000000000000004, 1e-300, 1e300, 9.3e18, -9.3e18]))
+_step = st.one_of(st.sampled_from([1.0, 0.5, 100.0, 0.7, -1.0, 37.5, 1e-3]), st.floats(min_value=1e-6, max_value=1e6))
+
+
+@settings(max_examples=400, deadline=None)
+@given(x=_f, y=_f, x_min=_f, y_min=_f, sx=_step, sy=_step, x_max=_f, y_max=_f)
+def test_point_to_pair_and_dimensions_agree_with_the_oracle_on_any_doubles(x, y, x_min, y_min, sx, sy, x_max, y_max):
+    """Go's int(float64) on amd64: truncation, NaN / out-of-range -> INT64_MIN (tools/utils.go:70-72, 133-137)"""
+    L = _lib.load()
+    r, c, orr, occ = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    _lib.check(L.v2r_idw_point_to_pair(x, y, x_min, sx, y_min, sy, C.byref(r), C.byref(c)))
+    O.lib().oracle_point_to_pair(x, y, x_min, sx, y_min, sy, C.byref(orr), C.byref(occ))
+    assert (r.value, c.value) == (orr.value, occ.value)
+    _lib.check(L.v2r_idw_get_dimensions(x_min, x_max, sx, y_min, y_max, sy, C.byref(r), C.byref(c)))
+    O.lib().oracle_get_dimensions(x_min, x_max, sx, y_min, y_max, sy, C.byref(orr), C.byref(occ))
+    assert (r.value, c.value) == (orr.value, occ.value)
+
+
+@settings(max_examples=60, deadline=None)
+@given(seed=st.integers(0, 2**32 - 1), n=st.integers(0, 400), cells=st.integers(1, 12), step=st.sampled_from([1.0, 0.25, 100.0]),
+       special=st.booleans())
+def test_make_coord_space_agrees_with_the_oracle_on_dense_collisions(seed, n, cells, step, special):
+    """few cells, many points: chains of the pairwise running average (new + old) / 2 in input order, keys outside the grid,
+    negative keys, and -- with `special` -- NaN / Inf coordinates whose key is Go's INT64_MIN"""
+    rng = np.random.default_rng(seed)
+    ext = cells * step
+    x, y, w = rng.uniform(-ext, 2 * ext, n), rng.uniform(-ext, 2 * ext, n), rng.normal(0, 1e3, n)
+    if special and n >= 4:
+        x[0], y[1], x[2], y[3] = np.nan, np.inf, -np.inf, np.nan
+    a = V.MakeCoordSpace(x, y, w, V.Info(0.0, ext - 1, step), V.Info(0.0, ext - 1, step))
+    b = O.make_coord_space(x, y, w, O.Info(0.0, ext - 1, step), O.Info(0.0, ext - 1, step))
+    assert len(a) == len(b)
+    for f in ("x", "y", "w", "key_r", "key_c"):
+        assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=f in ("x", "y", "w")), f
+
+
+@settings(max_examples=200, deadline=None)
+@given(es=st.floats(min_value=-5, max_value=10), span=st.floats(min_value=1e-3, max_value=12), ei=st.floats(min_value=1e-2, max_value=3))
+def test_exp_range_agrees_with_the_oracle(es, span, ei):
+    ee = es + span
+    if not ee > es:
+        return
+    assert np.array_equal(V.exp_range(es, ee, ei), O.exp_range(es, ee, ei))
